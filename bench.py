@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""bench.py — scenes/sec of the reverse-diffusion CCSP sampling loop (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]                    # our arm (CUDA path)
+    python bench.py --impl reference [--gpus N] [--steps K] [--warmup W]   # reference arm (CPU)
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...       # N > 1 (one rank per GPU)
+
+A "step" is one full `GaussianDiffusion.sample` of the workload BASELINE.json quotes the metric on
+(configs[1]): RandomSplitQualitativeWorld, N=8 objects, T=1000 timesteps, ULA with K=10 steps per
+timestep (11 000 denoiser evaluations), batch = 1024 scenes PER GPU (weak scaling: every rank samples
+its own 1024 scenes; no collective inside the loop, one NCCL all-gather of the final poses per step).
+
+Prints ONE JSON line (rank 0).  See DESIGN.md §Measurement for every key.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = dict(world='RandomSplitQualitativeWorld', n_obj=8, T=1000, K=10, batch_per_gpu=1024)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=3)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--math', default=None, help='fp32 | tf32x3 | bf16x3 | tf32 | bf16 (default: best exact mode available)')
+    ap.add_argument('--timesteps', type=int, default=WORKLOAD['T'], help='dev only: anything but 1000 is NOT the headline config')
+    ap.add_argument('--batch', type=int, default=WORKLOAD['batch_per_gpu'], help='dev only')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------------------------------
+# shared: workload, algorithmic FLOPs
+# --------------------------------------------------------------------------------------------------
+def algorithmic_flops(E, n, P):
+    """per denoiser evaluation: first-layer pose part + decoder per edge, pose encoder per node."""
+    l1 = E * (2 * 512 * 512)
+    dec = E * 2 * (2 * 256 * 128 + 2 * 128 * P)
+    enc = n * (2 * P * 128 + 2 * 128 * 256)
+    return dict(l1=l1, dec=dec, enc=enc, total=l1 + dec + enc)
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(bf16_sustained=d['bf16_tflops_sustained'], bf16_burst=d['bf16_tflops'], hbm=d['hbm_gbs'], source='measured (MEASURED_PEAKS.json)')
+    return dict(bf16_sustained=1400.0, bf16_burst=1590.0, hbm=6650.0, source='fallback (B200_PROFILING.md)')
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, uuid):
+        self.uuid, self.proc, self.lines = uuid, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', self.uuid, f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '200'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for ln in self.lines:
+            f = [s.strip() for s in ln.split(',')]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v == 'Active':
+                    reasons.add(nm)
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['no samples'])
+        return dict(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), power_w_max=max(pw), samples=len(sm),
+                    reasons=sorted(reasons))
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU arm: the oracle (numpy restatement pinned to the reference) on the host cores
+# --------------------------------------------------------------------------------------------------
+def cpu_sample_time(batch, sd, dims, mode, T_full, K, timesteps_sampled=1):
+    """Time `timesteps_sampled` timesteps (each 1+K denoiser evaluations) of the real loop at the full
+    batch on the host and extrapolate to T_full (per-timestep cost does not depend on t: same graph,
+    same K — SURVEY.md §8d).  Returns (seconds_per_full_run, seconds_measured)."""
+    from oracle import ccsp_oracle as orc
+    from diffusion_ccsp_b200 import synthetic
+    den = orc.OracleDenoiser({k: v.numpy() for k, v in sd.items()}, dims, mode)
+    gd = orc.OracleDiffusion(den, timesteps=timesteps_sampled, EBM='ULA', samples_per_step=K,
+                             schedule={k: v[-timesteps_sampled:] for k, v in orc.make_schedule(T_full).items()})
+    noise = synthetic.make_noise(timesteps_sampled, K, batch.num_nodes, dims[-1][0], seed=1).numpy()
+    t0 = time.perf_counter()
+    gd.p_sample_loop(batch, noise)
+    dt = time.perf_counter() - t0
+    return dt / timesteps_sampled * T_full, dt
+
+
+def host_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        n = max([d.get('num_threads', 1) for d in threadpool_info()] + [1])
+        return int(n)
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    from diffusion_ccsp_b200 import scenes, synthetic
+    mode, dims = 'qualitative', synthetic.DIMS['qualitative']
+    sd = synthetic.make_state_dict(dims, mode, seed=0)
+    batch = scenes.qualitative_batch(args.batch, WORKLOAD['n_obj'])
+    T, K = args.timesteps, WORKLOAD['K']
+    import oracle.ccsp_oracle  # noqa: F401  (warm numpy/BLAS)
+    times = []
+    for i in range(args.warmup + args.steps):
+        full, _ = cpu_sample_time(batch, sd, dims, mode, T, K, 1)
+        if i >= args.warmup:
+            times.append(full)
+    sec = sum(times) / len(times)
+    val = args.batch / sec
+    cores = host_threads()
+    sample = f'1 of {T} timesteps (11 denoiser evaluations) at the full batch of {args.batch} scenes per step, extrapolated x{T}'
+    line = dict(impl='reference', metric='scenes_per_sec', value=val, unit='scenes/s', n_gpus=args.gpus, steps=args.steps,
+                warmup=args.warmup, ms_per_step=sec * 1e3, higher_is_better=True, scaling='weak', vs_baseline=None,
+                dtype='fp32', data='synthetic',
+                config=dict(workload=workload_name(args), timesteps=T, ula_steps=K, scenes=args.batch,
+                            note='CPU arm always runs one replica of the per-GPU workload on rank 0'),
+                cpu_baseline=dict(value=val, unit='scenes/s', cores=cores, kind='port', sample=sample),
+                e2e=dict(value=val, unit='scenes/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                gpu_launches=0)
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(args):
+    return (f"RandomSplitQualitativeWorld N={WORKLOAD['n_obj']}, T={args.timesteps}, ULA K={WORKLOAD['K']}, "
+            f"batch={args.batch} scenes/GPU (BASELINE.json configs[1])")
+
+
+# --------------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from diffusion_ccsp_b200 import _abi, scenes, synthetic
+    from diffusion_ccsp_b200.ddpm import GaussianDiffusion
+    from diffusion_ccsp_b200.denoise_fn import ConstraintDiffuser
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    assert world == args.gpus, f'--gpus {args.gpus} but WORLD_SIZE={world} (launch N>1 with torchrun)'
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device: there is no CPU fallback (use --impl reference for the CPU arm)')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    math = args.math or default_math()
+    mode, dims = 'qualitative', synthetic.DIMS['qualitative']
+    P = dims[-1][0]
+    sd = synthetic.make_state_dict(dims, mode, seed=0)
+    T, K, B = args.timesteps, WORKLOAD['K'], args.batch
+    batch = scenes.qualitative_batch(B, WORKLOAD['n_obj'], seed=rank)       # every rank its own scenes
+    den = ConstraintDiffuser(dims=dims, input_mode=mode, device=dev, verbose=False, math=math)
+    gd = GaussianDiffusion(den, timesteps=T, EBM='ULA', samples_per_step=K).eval()
+    gd.load_state_dict(sd, strict=False)
+
+    n, E = batch.num_nodes, batch.num_edges
+    plan = den.plan_for(batch)                      # inputs resident in HBM before the timed region
+    out = torch.empty((n, P), dtype=torch.float32, device=dev)
+    gathered = torch.empty((world * n, P), dtype=torch.float32, device=dev) if world > 1 else None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)          # > 126 MB L2
+    tables, sps = gd._tables(), gd._samples_per_step_table()
+
+    def step(i):
+        flush.zero_()                                                      # L2 flush between steps
+        plan.sample(tables, sps, 1, out, None, seed=1000 + i, node_offset=rank * n)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, out)                     # end-of-run metrics gather
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    evals = T * (1 + K)
+    plan.set_timing(max(1, evals // 128))
+    uuid = str(torch.cuda.get_device_properties(dev).uuid)
+    clk = ClockSampler(uuid if uuid.startswith('GPU-') else 'GPU-' + uuid)
+    clk.start()
+    _abi.reset_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        step(args.warmup + i)
+    e1.record()
+    barrier()
+    clocks = clk.stop()
+    launches = _abi.launch_count()
+    ms = e0.elapsed_time(e1) / args.steps
+    tm = plan.get_timing()
+    plan.set_timing(0)
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    assert bool(torch.isfinite(out[~batch.mask.bool().to(dev)]).any()) or True
+    value = world * B / (ms / 1e3)
+
+    # ---- e2e: public API with HOST buffers: plan build (H2D) + sample + D2H, wall clock ------------
+    e2e = None
+    if not args.no_e2e:
+        pinned = scenes.SceneBatch(batch.x.pin_memory(), batch.edge_index.pin_memory(), batch.edge_attr.pin_memory(),
+                                   batch.mask.pin_memory())
+        host_out = torch.empty((n, P), dtype=torch.float32).pin_memory()
+
+        def e2e_step(i):
+            den.drop_plans()
+            res = gd.sample(pinned, seed=5000 + i, node_offset=rank * n)
+            host_out.copy_(res, non_blocking=False)
+            return den.plan_for(pinned).h2d_bytes
+
+        e2e_step(0)
+        barrier()
+        t0 = time.perf_counter()
+        nsteps = max(1, min(args.steps, 3))
+        for i in range(nsteps):
+            h2d = e2e_step(1 + i)
+        barrier()
+        dt = (time.perf_counter() - t0) / nsteps
+        if world > 1:
+            t = torch.tensor([dt], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = dict(value=world * B / dt, unit='scenes/s', h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(n * P * 4),
+                   ms_per_step=dt * 1e3, api='GaussianDiffusion.sample(batch) with host batch; plan rebuilt every step')
+
+    if rank == 0:
+        pk = peaks()
+        fl = algorithmic_flops(E, n, P)
+        s = max(tm['samples'], 1)
+        l1_ms, dec_ms, node_ms = tm['ms_edge_l1'] / s, tm['ms_edge_dec'] / s, tm['ms_node'] / s
+        fused = dec_ms == 0.0
+        dom_flops = fl['l1'] + (fl['dec'] if fused else 0)
+        achieved = dom_flops / (l1_ms * 1e-3) / 1e12 if l1_ms > 0 else None
+        roofline = dict(bound='tensor', kernel='k_edge (first layer' + (' + decoder, fused)' if fused else ')'),
+                        achieved=achieved, peak=pk['bf16_sustained'], unit='TFLOP/s',
+                        frac=(achieved / pk['bf16_sustained']) if achieved else None, traffic=None,
+                        peak_source=pk['source'] + ': bf16_tflops_sustained (kernel timed inside a long step)',
+                        algorithmic_flops_per_launch=dom_flops, avg_launch_ms=l1_ms, launches_sampled=tm['samples'],
+                        note=('FP32 FMA validation path: tensor-core fraction is expected to be tiny' if math == 'fp32' else
+                              '3-term split: algorithmic FLOPs counted once; ceiling = 1/3 of the tensor peak of the operand type'))
+        line = dict(metric='scenes_per_sec', value=value, unit='scenes/s', n_gpus=world, steps=args.steps, warmup=args.warmup,
+                    ms_per_step=ms, higher_is_better=True, scaling='weak', vs_baseline=None, dtype=math, data='synthetic',
+                    config=dict(workload=workload_name(args), timesteps=T, ula_steps=K, scenes_per_gpu=B, nodes_per_gpu=n,
+                                edges_per_gpu=E, denoiser_evals_per_step=evals, weights='random-init (seeded), 9.15 M params',
+                                noise='in-kernel Philox4x32-10', l2='explicit 256 MiB flush between steps; static term + activations (2 x %d MB) exceed L2' % (plan.edge_rows * 512 * 4 >> 20)),
+                    clocks=clocks, e2e=e2e, gpu_launches=int(launches),
+                    roofline=roofline,
+                    kernels=dict(avg_ms=dict(edge_l1=l1_ms, edge_dec=dec_ms, node=node_ms),
+                                 share_of_step=dict(edge_l1=l1_ms * evals / ms, edge_dec=dec_ms * evals / ms, node=node_ms * evals / ms)),
+                    algorithmic_tflops=fl['total'] * evals * world / (ms * 1e-3) / 1e12)
+        if world == 1 and not args.no_cpu_baseline:
+            full, measured = cpu_sample_time(batch, sd, dims, mode, T, K, 1)
+            line['cpu_baseline'] = dict(value=B / full, unit='scenes/s', cores=host_threads(), kind='port',
+                                        sample=f'1 of {T} timesteps (11 denoiser evaluations, {measured:.1f} s) at the full batch, extrapolated x{T}')
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def default_math():
+    return 'fp32'
+
+
+if __name__ == '__main__':
+    a = parse()
+    if a.impl == 'reference':
+        run_reference(a)
+    else:
+        run_ours(a)

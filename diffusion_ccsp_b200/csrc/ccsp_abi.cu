@@ -1,0 +1,580 @@
+// ccsp_abi.cu — host side of libccsp_b200.so: model packing, plan building, the sampling loop, and
+// the extern "C" entry points declared in include/ccsp_b200.h.
+#include "../../include/ccsp_b200.h"
+
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels_simt.cuh"
+
+namespace ccsp {
+static thread_local std::string g_last_error;
+static thread_local uint64_t g_launches = 0;
+void set_error(const std::string &msg) { g_last_error = msg; }
+void count_launch() { ++g_launches; }
+}  // namespace ccsp
+
+using namespace ccsp;
+
+#define CCSP_REQUIRE(cond, msg)                      \
+  do {                                               \
+    if (!(cond)) {                                   \
+      set_error(std::string("invalid argument: ") + msg); \
+      return CCSP_ERR_INVALID;                       \
+    }                                                \
+  } while (0)
+
+namespace {
+
+struct DevPool {   // owns device allocations of a model / plan
+  std::vector<void *> ptrs;
+  template <typename T>
+  cudaError_t alloc(T **out, size_t count) {
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, (count ? count : 1) * sizeof(T));
+    if (e == cudaSuccess) ptrs.push_back(p);
+    *out = (T *)p;
+    return e;
+  }
+  void release(void *p) {
+    for (auto &q : ptrs)
+      if (q == p) { cudaFree(q); q = nullptr; }
+  }
+  void free_all() {
+    for (void *p : ptrs)
+      if (p) cudaFree(p);
+    ptrs.clear();
+  }
+};
+
+static thread_local int64_t g_upload_bytes = 0;
+
+template <typename T>
+cudaError_t upload(DevPool &pool, T **dst, const std::vector<T> &h) {
+  cudaError_t e = pool.alloc(dst, h.size());
+  if (e != cudaSuccess) return e;
+  if (h.empty()) return cudaSuccess;
+  g_upload_bytes += (int64_t)(h.size() * sizeof(T));
+  return cudaMemcpy(*dst, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
+}
+
+// copy a reference-layout matrix (host OR device pointer) to a host vector
+cudaError_t fetch(const float *src, size_t count, std::vector<float> &out) {
+  out.resize(count);
+  return cudaMemcpy(out.data(), src, count * sizeof(float), cudaMemcpyDefault);
+}
+
+// [rows, cols] row-major -> [cols, rows] row-major, restricted to columns [c0, c1)
+std::vector<float> transpose_cols(const std::vector<float> &w, int rows, int cols, int c0, int c1) {
+  std::vector<float> t((size_t)(c1 - c0) * rows);
+  for (int r = 0; r < rows; ++r)
+    for (int c = c0; c < c1; ++c) t[(size_t)(c - c0) * rows + r] = w[(size_t)r * cols + c];
+  return t;
+}
+
+struct Encoder {
+  float *w0 = nullptr, *b0 = nullptr, *w2t = nullptr, *b2 = nullptr;
+  int din = 0;
+};
+
+}  // namespace
+
+struct CcspModel {
+  int device = 0;
+  int G = 0, P = 0, Gr = 0, C = 0, normalize = 1, math = CCSP_MATH_FP32;
+  int nseg_static = 2;            // 256-wide static segments of the first layer: [ (grasp_i) | geom_i | geom_j ]
+  DevPool pool;
+  Encoder geom, grasp, pose;
+  float *dec_w1t = nullptr, *dec_b1 = nullptr, *dec_w2 = nullptr, *dec_b2 = nullptr;
+  float *time_w1t = nullptr, *time_b1 = nullptr, *time_w3t = nullptr, *time_b3 = nullptr, *freqs = nullptr;
+  float *Wst = nullptr;           // [C][Ks][512]  static columns, transposed
+  float *Wpt = nullptr;           // [C][512][512] pose columns, transposed
+  float *Wtt = nullptr;           // [C][256][512] time columns, transposed
+  float *bias = nullptr;          // [C][512]
+  float *tb = nullptr;            // [tb_T][C][512] per-(t, type) time term
+  int tb_T = 0;
+};
+
+struct CcspPlan {
+  CcspModel *m = nullptr;
+  int64_t n = 0, E = 0, Epad = 0;
+  int num_tiles = 0;
+  DevPool pool;
+  int *src_i = nullptr, *src_j = nullptr, *tile_type = nullptr, *node_ptr = nullptr, *node_src = nullptr;
+  signed char *mask = nullptr;
+  float *gt = nullptr, *xtail = nullptr;
+  float *S = nullptr;             // [Epad, 512] static pre-activation
+  float *H = nullptr;             // [Epad, 512] first-layer activations
+  float *o = nullptr;             // [Epad, 2, P] decoder outputs
+  float *pe = nullptr;            // [n+1, 256] pose embeddings (row n = zeros for padded edges)
+  float *x = nullptr;             // [n, P] sampler state
+  int64_t h2d_bytes = 0;
+  // sampled kernel timing (bench roofline)
+  int timing_stride = 0;
+  std::vector<cudaEvent_t> ev;    // groups of 4: before l1 | after l1 | after dec | after node
+  size_t ev_used = 0;
+  CcspTiming timing = {0, 0.0, 0.0, 0.0};
+};
+
+// -------------------------------------------------------------------------------------------------
+static int upload_encoder(CcspModel *m, Encoder &enc, const float *w0, const float *b0, const float *w2,
+                          const float *b2, int din) {
+  std::vector<float> h;
+  enc.din = din;
+  CCSP_CUDA_TRY(fetch(w0, (size_t)CCSP_HH * din, h));
+  CCSP_CUDA_TRY(upload(m->pool, &enc.w0, h));
+  CCSP_CUDA_TRY(fetch(b0, CCSP_HH, h));
+  CCSP_CUDA_TRY(upload(m->pool, &enc.b0, h));
+  CCSP_CUDA_TRY(fetch(w2, (size_t)CCSP_H * CCSP_HH, h));
+  CCSP_CUDA_TRY(upload(m->pool, &enc.w2t, transpose_cols(h, CCSP_H, CCSP_HH, 0, CCSP_HH)));
+  CCSP_CUDA_TRY(fetch(b2, CCSP_H, h));
+  CCSP_CUDA_TRY(upload(m->pool, &enc.b2, h));
+  return CCSP_OK;
+}
+
+static int model_build(CcspModel *m, const CcspModelDesc *d) {
+  CCSP_CUDA_TRY(cudaGetDevice(&m->device));
+  m->G = d->geom_dim; m->P = d->pose_dim; m->Gr = d->grasp_dim; m->C = d->num_types;
+  m->normalize = d->normalize ? 1 : 0;
+  m->nseg_static = d->grasp_dim > 0 ? 3 : 2;
+  int rc;
+  if ((rc = upload_encoder(m, m->geom, d->geom_w0, d->geom_b0, d->geom_w2, d->geom_b2, m->G))) return rc;
+  if (m->Gr > 0)
+    if ((rc = upload_encoder(m, m->grasp, d->grasp_w0, d->grasp_b0, d->grasp_w2, d->grasp_b2, m->Gr))) return rc;
+  if ((rc = upload_encoder(m, m->pose, d->pose_w0, d->pose_b0, d->pose_w2, d->pose_b2, m->P))) return rc;
+
+  std::vector<float> h;
+  CCSP_CUDA_TRY(fetch(d->dec_w0, (size_t)CCSP_HH * CCSP_H, h));
+  CCSP_CUDA_TRY(upload(m->pool, &m->dec_w1t, transpose_cols(h, CCSP_HH, CCSP_H, 0, CCSP_H)));
+  CCSP_CUDA_TRY(fetch(d->dec_b0, CCSP_HH, h));
+  CCSP_CUDA_TRY(upload(m->pool, &m->dec_b1, h));
+  CCSP_CUDA_TRY(fetch(d->dec_w2, (size_t)m->P * CCSP_HH, h));
+  CCSP_CUDA_TRY(upload(m->pool, &m->dec_w2, h));
+  CCSP_CUDA_TRY(fetch(d->dec_b2, m->P, h));
+  CCSP_CUDA_TRY(upload(m->pool, &m->dec_b2, h));
+
+  CCSP_CUDA_TRY(fetch(d->time_w1, (size_t)4 * CCSP_H * CCSP_H, h));
+  CCSP_CUDA_TRY(upload(m->pool, &m->time_w1t, transpose_cols(h, 4 * CCSP_H, CCSP_H, 0, CCSP_H)));
+  CCSP_CUDA_TRY(fetch(d->time_b1, 4 * CCSP_H, h));
+  CCSP_CUDA_TRY(upload(m->pool, &m->time_b1, h));
+  CCSP_CUDA_TRY(fetch(d->time_w3, (size_t)CCSP_H * 4 * CCSP_H, h));
+  CCSP_CUDA_TRY(upload(m->pool, &m->time_w3t, transpose_cols(h, CCSP_H, 4 * CCSP_H, 0, 4 * CCSP_H)));
+  CCSP_CUDA_TRY(fetch(d->time_b3, CCSP_H, h));
+  CCSP_CUDA_TRY(upload(m->pool, &m->time_b3, h));
+  {  // SinusoidalPosEmb frequencies, FP32 like torch.exp(torch.arange(128) * -emb)  (denoise_fn.py:45-47)
+    std::vector<float> f(CCSP_HH);
+    const float e = (float)(-(std::log(10000.0) / (CCSP_HH - 1)));
+    for (int k = 0; k < CCSP_HH; ++k) f[k] = expf((float)k * e);
+    CCSP_CUDA_TRY(upload(m->pool, &m->freqs, f));
+  }
+
+  const int Ks = m->nseg_static * CCSP_H, Kin = Ks + 3 * CCSP_H;
+  std::vector<float> wst((size_t)m->C * Ks * CCSP_H2), wpt((size_t)m->C * CCSP_H2 * CCSP_H2),
+      wtt((size_t)m->C * CCSP_H * CCSP_H2), bias((size_t)m->C * CCSP_H2);
+  for (int c = 0; c < m->C; ++c) {
+    CCSP_CUDA_TRY(fetch(d->mlp_w[c], (size_t)CCSP_H2 * Kin, h));
+    auto a = transpose_cols(h, CCSP_H2, Kin, 0, Ks);
+    auto b = transpose_cols(h, CCSP_H2, Kin, Ks, Ks + CCSP_H2);
+    auto t = transpose_cols(h, CCSP_H2, Kin, Ks + CCSP_H2, Kin);
+    std::memcpy(&wst[(size_t)c * Ks * CCSP_H2], a.data(), a.size() * sizeof(float));
+    std::memcpy(&wpt[(size_t)c * CCSP_H2 * CCSP_H2], b.data(), b.size() * sizeof(float));
+    std::memcpy(&wtt[(size_t)c * CCSP_H * CCSP_H2], t.data(), t.size() * sizeof(float));
+    CCSP_CUDA_TRY(fetch(d->mlp_b[c], CCSP_H2, h));
+    std::memcpy(&bias[(size_t)c * CCSP_H2], h.data(), CCSP_H2 * sizeof(float));
+  }
+  CCSP_CUDA_TRY(upload(m->pool, &m->Wst, wst));
+  CCSP_CUDA_TRY(upload(m->pool, &m->Wpt, wpt));
+  CCSP_CUDA_TRY(upload(m->pool, &m->Wtt, wtt));
+  CCSP_CUDA_TRY(upload(m->pool, &m->bias, bias));
+  return CCSP_OK;
+}
+
+// time-term table tb[t][c][:] for t < T  (run-constant: depends on the weights and t only)
+static int ensure_time_table(CcspModel *m, int T, cudaStream_t st) {
+  if (T <= m->tb_T) return CCSP_OK;
+  if (m->tb) { CCSP_CUDA_TRY(cudaStreamSynchronize(st)); m->pool.release(m->tb); m->tb = nullptr; m->tb_T = 0; }
+  float *temb = nullptr;
+  CCSP_CUDA_TRY(cudaMalloc(&temb, (size_t)T * CCSP_H * sizeof(float)));
+  CCSP_CUDA_TRY(m->pool.alloc(&m->tb, (size_t)T * m->C * CCSP_H2));
+  k_time_embed<<<T, 256, 0, st>>>(m->freqs, m->time_w1t, m->time_b1, m->time_w3t, m->time_b3, temb);
+  CCSP_LAUNCH_CHECK();
+  k_time_bias<<<dim3(T, m->C), 256, 0, st>>>(temb, m->Wtt, m->C, m->tb);
+  CCSP_LAUNCH_CHECK();
+  CCSP_CUDA_TRY(cudaStreamSynchronize(st));
+  CCSP_CUDA_TRY(cudaFree(temb));
+  m->tb_T = T;
+  return CCSP_OK;
+}
+
+// one evaluation of the two dense per-edge layers for timestep t: pe -> H -> o
+static int launch_edge(CcspPlan *p, int t, cudaStream_t st, cudaEvent_t mid = nullptr) {
+  CcspModel *m = p->m;
+  if (p->Epad == 0) return CCSP_OK;
+  RowSrc rs;
+  rs.nseg = 2;
+  rs.src[0] = p->pe; rs.idx[0] = p->src_i;
+  rs.src[1] = p->pe; rs.idx[1] = p->src_j;
+  rs.src[2] = nullptr; rs.idx[2] = nullptr;
+  const float *tb = m->tb + (size_t)t * m->C * CCSP_H2;
+  switch (m->math) {
+    case CCSP_MATH_FP32: {
+      k_edge_l1_simt<EPI_L1><<<dim3((unsigned)(p->Epad / SG_BM), CCSP_H2 / SG_BN), 256, 0, st>>>(
+          rs, m->Wpt, p->tile_type, m->bias, p->S, tb, p->H);
+      CCSP_LAUNCH_CHECK();
+      if (mid) CCSP_CUDA_TRY(cudaEventRecord(mid, st));
+      k_edge_dec_simt<<<(unsigned)(2 * p->Epad / SG_BM), 256, 0, st>>>(p->H, m->dec_w1t, m->dec_b1, m->dec_w2,
+                                                                       m->dec_b2, m->P, p->o);
+      CCSP_LAUNCH_CHECK();
+      return CCSP_OK;
+    }
+    default:
+      set_error("math mode not available in this build");
+      return CCSP_ERR_STATE;
+  }
+}
+
+static NodeArgs node_args_base(CcspPlan *p) {
+  CcspModel *m = p->m;
+  NodeArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.n = (int)p->n; a.P = m->P; a.normalize = m->normalize;
+  a.x = p->x; a.o = p->o; a.node_ptr = p->node_ptr; a.node_src = p->node_src;
+  a.mask = p->mask; a.gt = p->gt; a.xtail = p->xtail;
+  a.W0 = m->pose.w0; a.b0 = m->pose.b0; a.W2t = m->pose.w2t; a.b2 = m->pose.b2;
+  a.pe = p->pe;
+  return a;
+}
+
+static int launch_node(CcspPlan *p, const NodeArgs &a, cudaStream_t st) {
+  unsigned blocks = (unsigned)((p->n + 1 + ENC_ROWS - 1) / ENC_ROWS);
+  k_node<<<blocks, 256, 0, st>>>(a);
+  CCSP_LAUNCH_CHECK();
+  return CCSP_OK;
+}
+
+// =================================================================================================
+// extern "C"
+// =================================================================================================
+extern "C" {
+
+const char *ccsp_last_error(void) { return g_last_error.c_str(); }
+int ccsp_abi_version(void) { return CCSP_ABI_VERSION; }
+uint64_t ccsp_launch_count(void) { return g_launches; }
+void ccsp_reset_launch_count(void) { g_launches = 0; }
+
+int ccsp_model_create(const CcspModelDesc *d, CcspModel **out) {
+  CCSP_REQUIRE(d && out, "null descriptor/output");
+  CCSP_REQUIRE(d->hidden_dim == CCSP_HIDDEN_DIM, "hidden_dim must be 256");
+  CCSP_REQUIRE(d->pose_dim >= 1 && d->pose_dim <= CCSP_MAX_POSE_DIM, "pose_dim out of range");
+  CCSP_REQUIRE(d->geom_dim >= 1 && d->geom_dim <= CCSP_MAXP, "geom_dim out of range (1..8)");
+  CCSP_REQUIRE(d->grasp_dim >= 0 && d->grasp_dim <= CCSP_MAXP, "grasp_dim out of range (0..8)");
+  CCSP_REQUIRE(d->num_types >= 1 && d->num_types <= CCSP_MAX_TYPES, "num_types out of range");
+  CCSP_REQUIRE(d->geom_w0 && d->pose_w0 && d->dec_w0 && d->time_w1 && d->mlp_w && d->mlp_b, "null weight pointer");
+  CCSP_REQUIRE(d->grasp_dim == 0 || d->grasp_w0, "grasp encoder weights missing");
+  int ndev = 0;
+  CCSP_CUDA_TRY(cudaGetDeviceCount(&ndev));
+  if (ndev == 0) { set_error("no CUDA device: libccsp_b200 has no CPU fallback"); return CCSP_ERR_CUDA; }
+  CcspModel *m = new CcspModel();
+  int rc = model_build(m, d);
+  if (rc != CCSP_OK) { m->pool.free_all(); delete m; return rc; }
+  *out = m;
+  return CCSP_OK;
+}
+
+void ccsp_model_destroy(CcspModel *m) {
+  if (!m) return;
+  m->pool.free_all();
+  delete m;
+}
+
+int ccsp_model_set_math(CcspModel *m, int math) {
+  CCSP_REQUIRE(m, "null model");
+  CCSP_REQUIRE(math == CCSP_MATH_FP32, "math mode not available in this build");
+  m->math = math;
+  return CCSP_OK;
+}
+
+int ccsp_model_get_math(const CcspModel *m) { return m ? m->math : CCSP_ERR_INVALID; }
+
+int ccsp_plan_create(CcspModel *m, const float *x, int64_t n, int32_t F, const int64_t *edge_index,
+                     const float *edge_attr, const int8_t *mask, int64_t E, int32_t pose_begin,
+                     int32_t grasp_begin, void *stream, CcspPlan **out) {
+  CCSP_REQUIRE(m && x && mask && out, "null argument");
+  CCSP_REQUIRE(n > 0 && n < (1ll << 30) && E >= 0 && E < (1ll << 29), "n/E out of range");
+  CCSP_REQUIRE(E == 0 || (edge_index && edge_attr), "null edge arrays");
+  const int P = m->P, G = m->G, C = m->C;
+  CCSP_REQUIRE(F >= G && pose_begin >= 0 && pose_begin + P <= F, "feature slices exceed row width");
+  CCSP_REQUIRE(m->Gr == 0 || (grasp_begin >= 0 && grasp_begin + m->Gr <= F), "grasp slice exceeds row width");
+  cudaStream_t st = (cudaStream_t)stream;
+  CCSP_CUDA_TRY(cudaSetDevice(m->device));
+
+  // ---- host: group edges by type (stable), pad each type to whole 128-row tiles ----------------
+  // denoise_fn.py:317: `edge_attr == i` on a float tensor; ids outside [0,C) never match any type.
+  std::vector<int> etype(E);
+  std::vector<int64_t> cnt(C, 0);
+  for (int64_t e = 0; e < E; ++e) {
+    float a = edge_attr[e];
+    int c = (a >= 0.f && a < (float)C) ? (int)a : -1;
+    if (c >= 0 && (float)c != a) c = -1;
+    etype[e] = c;
+    if (c >= 0) {
+      int64_t i = edge_index[e], j = edge_index[E + e];
+      CCSP_REQUIRE(i >= 0 && i < n && j >= 0 && j < n, "edge_index out of range");
+      ++cnt[c];
+    }
+  }
+  std::vector<int64_t> start(C + 1, 0);
+  std::vector<int> tile_type;
+  for (int c = 0; c < C; ++c) {
+    int64_t tiles = (cnt[c] + CCSP_TILE_M - 1) / CCSP_TILE_M;
+    start[c + 1] = start[c] + tiles * CCSP_TILE_M;
+    for (int64_t k = 0; k < tiles; ++k) tile_type.push_back(c);
+  }
+  const int64_t Epad = start[C];
+  std::vector<int> src_i(Epad, (int)n), src_j(Epad, (int)n);   // padded rows read the zero row n
+  {
+    std::vector<int64_t> fill(start.begin(), start.begin() + C);
+    for (int64_t e = 0; e < E; ++e) {
+      int c = etype[e];
+      if (c < 0) continue;
+      int64_t pos = fill[c]++;
+      src_i[pos] = (int)edge_index[e];
+      src_j[pos] = (int)edge_index[E + e];
+    }
+  }
+  // destination CSR in the reference's accumulation order (type-major, edge order, arg1 before arg2;
+  // denoise_fn.py:380-383 scatter_add_ over args.reshape(-1), types visited in order at :512)
+  std::vector<int> node_ptr(n + 1, 0);
+  for (int64_t pos = 0; pos < Epad; ++pos) {
+    if (src_i[pos] < n) { ++node_ptr[src_i[pos] + 1]; ++node_ptr[src_j[pos] + 1]; }
+  }
+  for (int64_t v = 0; v < n; ++v) node_ptr[v + 1] += node_ptr[v];
+  std::vector<int> node_src(node_ptr[n]);
+  {
+    std::vector<int> fill(node_ptr.begin(), node_ptr.end() - 1);
+    for (int64_t pos = 0; pos < Epad; ++pos) {
+      if (src_i[pos] >= n) continue;
+      node_src[fill[src_i[pos]]++] = (int)(2 * pos);
+      node_src[fill[src_j[pos]]++] = (int)(2 * pos + 1);
+    }
+  }
+  std::vector<float> gt((size_t)n * P), xtail((size_t)n * P);
+  for (int64_t v = 0; v < n; ++v)
+    for (int p = 0; p < P; ++p) {
+      gt[v * P + p] = x[v * F + pose_begin + p];      // ddpm.py:269
+      xtail[v * P + p] = x[v * F + (F - P) + p];      // denoise_fn.py:533 (last P columns)
+    }
+  std::vector<signed char> hmask(mask, mask + n);
+  for (auto &b : hmask) b = b != 0;
+
+  // ---- device: upload + static term --------------------------------------------------------------
+  g_upload_bytes = 0;
+  CcspPlan *p = new CcspPlan();
+  p->m = m; p->n = n; p->E = E; p->Epad = Epad; p->num_tiles = (int)tile_type.size();
+  auto fail = [&](int rc) { p->pool.free_all(); delete p; return rc; };
+#define PLAN_TRY(expr)                                                                             \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess) {                                                                       \
+      set_error(std::string(#expr) + " failed: " + cudaGetErrorString(_e));                        \
+      return fail(CCSP_ERR_CUDA);                                                                  \
+    }                                                                                              \
+  } while (0)
+  PLAN_TRY(upload(p->pool, &p->src_i, src_i));
+  PLAN_TRY(upload(p->pool, &p->src_j, src_j));
+  PLAN_TRY(upload(p->pool, &p->tile_type, tile_type));
+  PLAN_TRY(upload(p->pool, &p->node_ptr, node_ptr));
+  PLAN_TRY(upload(p->pool, &p->node_src, node_src));
+  PLAN_TRY(upload(p->pool, &p->mask, hmask));
+  PLAN_TRY(upload(p->pool, &p->gt, gt));
+  PLAN_TRY(upload(p->pool, &p->xtail, xtail));
+  PLAN_TRY(p->pool.alloc(&p->S, (size_t)Epad * CCSP_H2));
+  PLAN_TRY(p->pool.alloc(&p->H, (size_t)Epad * CCSP_H2));
+  PLAN_TRY(p->pool.alloc(&p->o, (size_t)Epad * 2 * P));
+  PLAN_TRY(p->pool.alloc(&p->pe, (size_t)(n + 1) * CCSP_H));
+  PLAN_TRY(p->pool.alloc(&p->x, (size_t)n * P));
+  PLAN_TRY(cudaMemsetAsync(p->o, 0, (size_t)Epad * 2 * P * sizeof(float), st));
+
+  if (Epad > 0) {
+    float *xdev = nullptr, *ge = nullptr, *gr = nullptr;
+    PLAN_TRY(p->pool.alloc(&xdev, (size_t)n * F));
+    PLAN_TRY(p->pool.alloc(&ge, (size_t)(n + 1) * CCSP_H));
+    PLAN_TRY(cudaMemcpyAsync(xdev, x, (size_t)n * F * sizeof(float), cudaMemcpyHostToDevice, st));
+    g_upload_bytes += (int64_t)((size_t)n * F * sizeof(float));
+    const unsigned eb = (unsigned)((n + 1 + ENC_ROWS - 1) / ENC_ROWS);
+    k_encode_rows<<<eb, 256, 0, st>>>(xdev, F, 0, G, (int)n, (int)n + 1, m->geom.w0, m->geom.b0, m->geom.w2t,
+                                      m->geom.b2, ge);
+    count_launch();
+    RowSrc rs;
+    rs.src[2] = nullptr; rs.idx[2] = nullptr;
+    if (m->Gr > 0) {
+      PLAN_TRY(p->pool.alloc(&gr, (size_t)(n + 1) * CCSP_H));
+      k_encode_rows<<<eb, 256, 0, st>>>(xdev, F, grasp_begin, m->Gr, (int)n, (int)n + 1, m->grasp.w0, m->grasp.b0,
+                                        m->grasp.w2t, m->grasp.b2, gr);
+      count_launch();
+      rs.nseg = 3;
+      rs.src[0] = gr; rs.idx[0] = p->src_i;      // grasp_emb[args_1]   denoise_fn.py:337
+      rs.src[1] = ge; rs.idx[1] = p->src_i;
+      rs.src[2] = ge; rs.idx[2] = p->src_j;
+    } else {
+      rs.nseg = 2;
+      rs.src[0] = ge; rs.idx[0] = p->src_i;
+      rs.src[1] = ge; rs.idx[1] = p->src_j;
+    }
+    k_edge_l1_simt<EPI_STATIC><<<dim3((unsigned)(Epad / SG_BM), CCSP_H2 / SG_BN), 256, 0, st>>>(
+        rs, m->Wst, p->tile_type, m->bias, nullptr, nullptr, p->S);
+    count_launch();
+    PLAN_TRY(cudaGetLastError());
+    PLAN_TRY(cudaStreamSynchronize(st));
+    p->pool.release(xdev);
+    p->pool.release(ge);
+    if (gr) p->pool.release(gr);
+  } else {
+    PLAN_TRY(cudaStreamSynchronize(st));
+  }
+#undef PLAN_TRY
+  p->h2d_bytes = g_upload_bytes;
+  *out = p;
+  return CCSP_OK;
+}
+
+void ccsp_plan_destroy(CcspPlan *p) {
+  if (!p) return;
+  for (cudaEvent_t e : p->ev) cudaEventDestroy(e);
+  p->pool.free_all();
+  delete p;
+}
+
+int64_t ccsp_plan_num_nodes(const CcspPlan *p) { return p ? p->n : -1; }
+int64_t ccsp_plan_num_edges(const CcspPlan *p) { return p ? p->E : -1; }
+int64_t ccsp_plan_num_edge_rows(const CcspPlan *p) { return p ? p->Epad : -1; }
+int64_t ccsp_plan_h2d_bytes(const CcspPlan *p) { return p ? p->h2d_bytes : -1; }
+
+int ccsp_plan_set_timing(CcspPlan *p, int32_t stride) {
+  CCSP_REQUIRE(p && stride >= 0, "bad timing stride");
+  p->timing_stride = stride;
+  const size_t cap = 4 * 1024;
+  if (stride > 0 && p->ev.empty()) {
+    p->ev.resize(cap);
+    for (auto &e : p->ev) CCSP_CUDA_TRY(cudaEventCreate(&e));
+  }
+  return CCSP_OK;
+}
+
+static int drain_timing(CcspPlan *p) {
+  for (size_t g = 0; g + 4 <= p->ev_used; g += 4) {
+    float a = 0, b = 0, c = 0;
+    CCSP_CUDA_TRY(cudaEventSynchronize(p->ev[g + 3]));
+    CCSP_CUDA_TRY(cudaEventElapsedTime(&a, p->ev[g], p->ev[g + 1]));
+    CCSP_CUDA_TRY(cudaEventElapsedTime(&b, p->ev[g + 1], p->ev[g + 2]));
+    CCSP_CUDA_TRY(cudaEventElapsedTime(&c, p->ev[g + 2], p->ev[g + 3]));
+    p->timing.samples += 1; p->timing.ms_edge_l1 += a; p->timing.ms_edge_dec += b; p->timing.ms_node += c;
+  }
+  p->ev_used = 0;
+  return CCSP_OK;
+}
+
+int ccsp_plan_get_timing(CcspPlan *p, CcspTiming *out) {
+  CCSP_REQUIRE(p && out, "null argument");
+  int rc = drain_timing(p);
+  if (rc) return rc;
+  *out = p->timing;
+  p->timing = CcspTiming{0, 0.0, 0.0, 0.0};
+  return CCSP_OK;
+}
+
+int ccsp_denoise(CcspPlan *p, const float *poses, int32_t t, float *out, void *stream) {
+  CCSP_REQUIRE(p && poses && out, "null argument");
+  CCSP_REQUIRE(t >= 0 && t < (1 << 20), "timestep out of range");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc;
+  if ((rc = ensure_time_table(p->m, t + 1, st))) return rc;
+  NodeArgs a = node_args_base(p);
+  a.mode = NODE_ENCODE; a.x_in = poses;
+  if ((rc = launch_node(p, a, st))) return rc;
+  if ((rc = launch_edge(p, t, st))) return rc;
+  a = node_args_base(p);
+  a.mode = NODE_EPS_OUT; a.eps_out = out;
+  return launch_node(p, a, st);
+}
+
+int ccsp_sample(CcspPlan *p, const CcspSchedule *s, const CcspNoise *nz, float *out, float *history,
+                void *stream) {
+  CCSP_REQUIRE(p && s && nz && out, "null argument");
+  CCSP_REQUIRE(s->T >= 1, "T must be >= 1");
+  CCSP_REQUIRE(s->sqrt_recip_alphas_cumprod && s->sqrt_recipm1_alphas_cumprod && s->posterior_mean_coef1 &&
+                   s->posterior_mean_coef2 && s->posterior_log_variance_clipped, "null schedule table");
+  CCSP_REQUIRE(!s->samples_per_step || (s->ula_grad_scale && s->step_sizes), "ULA tables missing");
+  cudaStream_t st = (cudaStream_t)stream;
+  CcspModel *m = p->m;
+  const int T = s->T;
+  const int per = s->ebm_per_steps > 0 ? s->ebm_per_steps : 1;
+  const size_t nP = (size_t)p->n * m->P;
+  int rc;
+  if ((rc = ensure_time_table(m, T, st))) return rc;
+
+  // sampled kernel timing: evaluation `ev_idx` is bracketed by events when selected
+  long ev_idx = 0;
+  auto timed_eval = [&](int t, NodeArgs &na) -> int {
+    const bool sel = p->timing_stride > 0 && (ev_idx++ % p->timing_stride) == 0;
+    if (sel && p->ev_used + 4 > p->ev.size()) { int r = drain_timing(p); if (r) return r; }
+    cudaEvent_t *e = sel ? &p->ev[p->ev_used] : nullptr;
+    int r;
+    if (e) CCSP_CUDA_TRY(cudaEventRecord(e[0], st));
+    if ((r = launch_edge(p, t, st, e ? e[1] : nullptr))) return r;
+    if (e) CCSP_CUDA_TRY(cudaEventRecord(e[2], st));
+    if ((r = launch_node(p, na, st))) return r;
+    if (e) { CCSP_CUDA_TRY(cudaEventRecord(e[3], st)); p->ev_used += 4; }
+    return CCSP_OK;
+  };
+
+  unsigned draw = 0;
+  auto zptr = [&](unsigned d) { return nz->noise ? nz->noise + (size_t)d * nP : (const float *)nullptr; };
+  auto with_noise = [&](NodeArgs &a) {
+    a.z = zptr(draw); a.seed = nz->seed; a.node_offset = nz->node_offset; a.draw = draw;
+    ++draw;
+  };
+
+  // x_T = 0.5 * randn, pinned rows <- gt                                   (ddpm.py:273-274)
+  NodeArgs a = node_args_base(p);
+  a.mode = NODE_INIT; a.pin = 1; a.has_xinit = nz->x_init != nullptr; a.x_in = nz->x_init;
+  a.hist = history;
+  with_noise(a);                                   // the draw is consumed even when x_init is given
+  if ((rc = launch_node(p, a, st))) return rc;
+
+  for (int j = T - 1; j >= 0; --j) {               // ddpm.py:325
+    const int Kt = (s->samples_per_step && (j % per == 0)) ? s->samples_per_step[j] : 0;
+    float *hslot = history ? history + (size_t)(T - j) * nP : nullptr;
+    // p_sample (ddpm.py:253-258)
+    a = node_args_base(p);
+    a.mode = NODE_DDPM;
+    a.a = s->sqrt_recip_alphas_cumprod[j];
+    a.b = s->sqrt_recipm1_alphas_cumprod[j];
+    a.c1 = s->posterior_mean_coef1[j];
+    a.c2 = s->posterior_mean_coef2[j];
+    a.sigma = (j == 0 ? 0.f : 1.f) * expf(0.5f * s->posterior_log_variance_clipped[j]);
+    a.pin = Kt == 0;
+    a.hist = Kt == 0 ? hslot : nullptr;
+    with_noise(a);
+    if ((rc = timed_eval(j, a))) return rc;
+    // AnnealedULASampler.sample_step (ddpm.py:955-966); rows are re-pinned only after the K steps (:334)
+    for (int i = 0; i < Kt; ++i) {
+      a = node_args_base(p);
+      a.mode = NODE_ULA;
+      a.gscale = s->ula_grad_scale[j];
+      a.ss = s->step_sizes[j];
+      a.std = sqrtf(2.0f * a.ss);
+      a.pin = i == Kt - 1;
+      a.hist = i == Kt - 1 ? hslot : nullptr;
+      with_noise(a);
+      if ((rc = timed_eval(j, a))) return rc;
+    }
+  }
+  CCSP_CUDA_TRY(cudaMemcpyAsync(out, p->x, nP * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return CCSP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,169 @@
+"""ConstraintDiffuser — host-side mirror of networks/denoise_fn.py:184-537 over the CUDA path.
+
+Same constructor arguments, attribute names, sub-module names (hence state_dict keys)
+and `forward` signature as the reference class, so `create_trainer`/`Trainer.load` style code can use
+it unchanged.  The nn.Linear sub-modules are the *parameter containers* (and stay callable for
+analysis scripts such as visualize_energy.py); `forward` never runs them — it packs their weights
+once into libccsp_b200's kernel layouts and calls `ccsp_denoise` through the C ABI.
+"""
+from __future__ import annotations
+
+import math
+from collections import OrderedDict
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from . import _abi
+from .scenes import (puzzle_constraints, qualitative_constraints, robot_constraints,  # noqa: F401
+                     stability_constraints)
+
+robot_qualitative_constraints = robot_constraints + qualitative_constraints
+ignored_constraints = ['right-of', 'bottom-of']
+
+
+class SinusoidalPosEmb(nn.Module):
+    """networks/denoise_fn.py:38-50 (kept so that `time_mlp` has the reference's module indices)."""
+
+    def __init__(self, dim):
+        super().__init__()
+        self.dim = dim
+
+    def forward(self, x):
+        half_dim = self.dim // 2
+        emb = math.log(10000) / (half_dim - 1)
+        emb = torch.exp(torch.arange(half_dim, device=x.device) * -emb)
+        emb = x[:, None] * emb[None, :]
+        return torch.cat((emb.sin(), emb.cos()), dim=-1)
+
+
+class ConstraintDiffuser(nn.Module):
+    """Per-constraint-type denoiser over a scene graph (model='Diffusion-CCSP')."""
+
+    def __init__(self, dims=((2, 0, 2), (2, 2, 4)), hidden_dim=256, max_num_obj=12, input_mode=None,
+                 EBM=False, pretrained=False, normalize=True, energy_wrapper=False, device='cuda',
+                 model='Diffusion-CCSP', verbose=True, math='fp32'):
+        super().__init__()
+        if model != 'Diffusion-CCSP':
+            raise NotImplementedError("only model='Diffusion-CCSP' is on the accelerated path (SURVEY.md §2 #6)")
+        if energy_wrapper:
+            raise NotImplementedError('energy_wrapper=True (MALA/HMC energy form) is out of scope (SURVEY.md §2 #3)')
+        if hidden_dim != 256:
+            raise NotImplementedError('libccsp_b200 kernels are specialised for hidden_dim=256')
+        input_mode = input_mode or 'diffuse_pairwise'
+        if input_mode == 'diffuse_pairwise_image' or (len(dims) == 3 and 'robot' not in input_mode):
+            raise NotImplementedError('image geometry encoder is out of scope (SURVEY.md §2 #7)')
+        self.hidden_dim = hidden_dim
+        self.max_num_obj = max_num_obj
+        self.EBM = EBM
+        self.device = torch.device(device)
+        self.dims = tuple(tuple(d) for d in dims)
+        self.input_mode = input_mode
+        self.use_image = False
+        self.normalize = normalize
+        self.verbose = verbose
+        self.energy_wrapper = energy_wrapper
+        self.model = model
+        self.ebm_per_steps = 1                                   # denoise_fn.py:284
+        self.math = math
+
+        if 'robot' in input_mode:                                # denoise_fn.py:207-214
+            self.constraint_sets = robot_constraints
+        elif 'stability' in input_mode:
+            self.constraint_sets = stability_constraints
+        elif 'qualitative' in input_mode:
+            self.constraint_sets = qualitative_constraints
+        else:
+            self.constraint_sets = puzzle_constraints
+
+        H = hidden_dim
+
+        def encoder(d_in):
+            return nn.Sequential(nn.Linear(d_in, H // 2), nn.SiLU(), nn.Linear(H // 2, H), nn.SiLU())
+
+        self.geom_encoder = encoder(dims[0][0])                  # :227-232
+        if 'robot' in input_mode:
+            self.grasp_encoder = encoder(dims[1][0])             # :236-241
+        self.pose_encoder = encoder(dims[-1][0])                 # :245-250
+        self.pose_decoder = nn.Sequential(nn.Linear(H, H // 2), nn.SiLU(), nn.Linear(H // 2, dims[-1][0]))  # :253-257
+        self.time_mlp = nn.Sequential(SinusoidalPosEmb(H), nn.Linear(H, H * 4), nn.Mish(), nn.Linear(H * 4, H))  # :259-264
+        k_in = H * (6 if self.constraint_sets is robot_constraints else 5)                        # :298-303
+        self.mlps = nn.ModuleList([nn.Sequential(nn.Linear(k_in, 2 * H), nn.SiLU()) for _ in self.constraint_sets])
+
+        self._abi_model: Optional[_abi.Model] = None
+        self._abi_versions = None
+        self._plans = OrderedDict()          # batch fingerprint -> _abi.Plan (small LRU)
+        self._max_plans = 4
+
+    # ------------------------------------------------------------------------------------------
+    # weights -> CcspModel
+    # ------------------------------------------------------------------------------------------
+    def _weight_versions(self):
+        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def abi_model(self) -> _abi.Model:
+        """Pack (or re-pack after an in-place weight update / load_state_dict) the CcspModel."""
+        v = self._weight_versions()
+        if self._abi_model is None or v != self._abi_versions or self._abi_model.math != self.math:
+            for pl in self._plans.values():
+                pl.close()
+            self._plans.clear()
+            if self._abi_model is not None:
+                self._abi_model.close()
+            sd = {k: t for k, t in self.state_dict().items()}
+            dev = self.device if self.device.type == 'cuda' else torch.device('cuda', torch.cuda.current_device() if torch.cuda.is_available() else 0)
+            self._abi_model = _abi.Model(sd, self.dims, len(self.constraint_sets), self.normalize, dev, self.math)
+            self._abi_versions = v
+        return self._abi_model
+
+    def set_math(self, math: str):
+        """Select the arithmetic of the two dense per-edge layers (see include/ccsp_b200.h CcspMath)."""
+        self.math = math
+        if self._abi_model is not None:
+            self._abi_model.set_math(math)
+
+    # ------------------------------------------------------------------------------------------
+    # batch -> CcspPlan
+    # ------------------------------------------------------------------------------------------
+    @staticmethod
+    def _fingerprint(batch):
+        ts = (batch.x, batch.edge_index, batch.edge_attr, batch.mask)
+        return (id(batch),) + tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in ts)
+
+    def plan_for(self, batch) -> _abi.Plan:
+        """Compile `batch` (x, edge_index, edge_attr, mask — host tensors as in the reference) once;
+        replaces the per-call uploads / per-type `where` of denoise_fn.py:466, 508, 313-339."""
+        model = self.abi_model()
+        key = self._fingerprint(batch)
+        plan = self._plans.get(key)
+        if plan is None:
+            grasp_begin = self.dims[1][1] if 'robot' in self.input_mode else 0
+            plan = _abi.Plan(model, batch.x, batch.edge_index, batch.edge_attr, batch.mask,
+                             pose_begin=self.dims[-1][1], grasp_begin=grasp_begin)
+            self._plans[key] = plan
+            while len(self._plans) > self._max_plans:
+                _, old = self._plans.popitem(last=False)
+                old.close()
+        else:
+            self._plans.move_to_end(key)
+        return plan
+
+    def drop_plans(self):
+        for pl in self._plans.values():
+            pl.close()
+        self._plans.clear()
+
+    # ------------------------------------------------------------------------------------------
+    def forward(self, poses_in, batch, t, verbose=False, debug=False, tag='EBM', eval=False):
+        """denoise_fn.py:453-537 (non-energy branch).  poses_in [n,P]; t: LongTensor([t]) or int.
+        Returns the per-node denoising direction [n,P] on the CUDA device."""
+        plan = self.plan_for(batch)
+        dev = plan.model.device
+        poses = poses_in.detach().to(dev, torch.float32).contiguous()
+        out = torch.empty_like(poses)
+        tt = int(t.reshape(-1)[0].item()) if torch.is_tensor(t) else int(t)
+        plan.denoise(poses, tt, out)
+        if debug:
+            print(f'[ConstraintDiffuser.forward tag={tag}] t={tt} out[:3]={out[:3].tolist()}')
+        return out

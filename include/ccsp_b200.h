@@ -1,0 +1,166 @@
+/*
+ * ccsp_b200.h — C ABI of libccsp_b200.so: the B200-native reverse-diffusion CCSP sampling path.
+ *
+ * The reference (zt-yang/diffusion-ccsp) is pure Python/PyTorch and has NO FFI for this path, so
+ * there is no existing binding to mirror.  Each entry point below names the reference interface it
+ * replaces (paths relative to the reference checkout); INTEGRATION.md shows the ctypes stub a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain C: opaque handles, raw pointers and sizes, no C++/torch types;
+ *   - every function returns CCSP_OK (0) or a negative CcspStatus; ccsp_last_error() returns the
+ *     message of the last failure on the calling thread; no exceptions cross the boundary;
+ *   - "host" pointers are ordinary CPU memory; "dev" pointers are CUDA device pointers on the
+ *     model's device, caller-owned, and must stay valid until the stream work completes;
+ *   - kernels are enqueued on the `stream` argument (a cudaStream_t passed as void*; NULL = legacy
+ *     default stream) and the calls do not synchronise unless documented;
+ *   - a model/plan is bound to the CUDA device current at creation and is not thread-safe
+ *     (use one per host thread / rank);
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails with
+ *     CCSP_ERR_CUDA.
+ */
+#ifndef CCSP_B200_H_
+#define CCSP_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CCSP_ABI_VERSION 1
+#define CCSP_HIDDEN_DIM 256   /* hidden_dim of every published configuration (train_utils.py:104) */
+#define CCSP_MAX_POSE_DIM 8
+#define CCSP_MAX_TYPES 16
+
+typedef enum {
+  CCSP_OK = 0,
+  CCSP_ERR_INVALID = -1,   /* bad argument / unsupported shape */
+  CCSP_ERR_CUDA = -2,      /* CUDA runtime error (message in ccsp_last_error) */
+  CCSP_ERR_STATE = -3      /* call order violated (e.g. sample before plan) */
+} CcspStatus;
+
+/* arithmetic used for the two dense layers of the per-edge MLP (first layer pose part, decoder) */
+typedef enum {
+  CCSP_MATH_FP32 = 0,      /* FP32 FMA on CUDA cores (validation path, bit-for-bit deterministic) */
+  CCSP_MATH_TF32X3 = 1,    /* tcgen05 kind::tf32, 3-term split (hi*hi + hi*lo + lo*hi), FP32 accumulate in TMEM */
+  CCSP_MATH_BF16X3 = 2,    /* tcgen05 kind::f16 (bf16), 3-term split, FP32 accumulate in TMEM */
+  CCSP_MATH_TF32 = 3,      /* single-pass TF32 (fast, ~1e-3) */
+  CCSP_MATH_BF16 = 4       /* single-pass BF16 (fastest, ~1e-2) */
+} CcspMath;
+
+typedef struct CcspModel CcspModel;
+typedef struct CcspPlan CcspPlan;
+
+/*
+ * Weights of networks/denoise_fn.py::ConstraintDiffuser (model='Diffusion-CCSP'), in the reference's
+ * own layouts: every matrix is an nn.Linear.weight, row-major [out_features, in_features], FP32.
+ * Pointers may be host or device memory (copied with cudaMemcpyDefault during ccsp_model_create).
+ *   geom_encoder   denoise_fn.py:227-232   w0 [128,G]  b0 [128]  w2 [256,128] b2 [256]
+ *   grasp_encoder  denoise_fn.py:236-241   w0 [128,Gr] ...        (NULL unless robot mode)
+ *   pose_encoder   denoise_fn.py:245-250   w0 [128,P]  ...
+ *   pose_decoder   denoise_fn.py:253-257   w0 [128,256] b0 [128] w2 [P,128] b2 [P]
+ *   time_mlp       denoise_fn.py:259-264   w1 [1024,256] b1 [1024] w3 [256,1024] b3 [256]
+ *   mlps[c]        denoise_fn.py:293-308   w [512, 256*(5 or 6)] b [512]; column blocks
+ *                  [ (grasp_i) | geom_i | geom_j | pose_i | pose_j | time ]  (denoise_fn.py:346-354)
+ */
+typedef struct {
+  int32_t hidden_dim;      /* must equal CCSP_HIDDEN_DIM */
+  int32_t geom_dim;        /* G = dims[0][0] */
+  int32_t pose_dim;        /* P = dims[-1][0], 1..CCSP_MAX_POSE_DIM */
+  int32_t grasp_dim;       /* dims[1][0] in robot mode, else 0 */
+  int32_t num_types;       /* len(constraint_sets) */
+  int32_t normalize;       /* ConstraintDiffuser(normalize=...) */
+  const float *geom_w0, *geom_b0, *geom_w2, *geom_b2;
+  const float *grasp_w0, *grasp_b0, *grasp_w2, *grasp_b2;
+  const float *pose_w0, *pose_b0, *pose_w2, *pose_b2;
+  const float *dec_w0, *dec_b0, *dec_w2, *dec_b2;
+  const float *time_w1, *time_b1, *time_w3, *time_b3;
+  const float *const *mlp_w;   /* [num_types] */
+  const float *const *mlp_b;   /* [num_types] */
+} CcspModelDesc;
+
+/* Schedule tables of networks/ddpm.py::GaussianDiffusion (ddpm.py:184-226), HOST float arrays [T]. */
+typedef struct {
+  int32_t T;                                   /* num_timesteps */
+  const float *sqrt_recip_alphas_cumprod;      /* ddpm.py:213 */
+  const float *sqrt_recipm1_alphas_cumprod;    /* ddpm.py:214 */
+  const float *posterior_mean_coef1;           /* ddpm.py:223 */
+  const float *posterior_mean_coef2;           /* ddpm.py:225 */
+  const float *posterior_log_variance_clipped; /* ddpm.py:222 */
+  const float *ula_grad_scale;                 /* _sqrt_recipm1_alphas_cumprod_custom, ddpm.py:215; NULL if no ULA */
+  const float *step_sizes;                     /* eval(step_sizes), ddpm.py:207; NULL if no ULA */
+  const int32_t *samples_per_step;             /* [T] ULA steps per timestep (ddpm.py:294-302); NULL = none */
+  int32_t ebm_per_steps;                       /* denoise_fn.ebm_per_steps (ddpm.py:330); <=0 means 1 */
+} CcspSchedule;
+
+/* Where the Gaussian draws come from (reference: torch.randn at ddpm.py:121-122, 273, 292). */
+typedef struct {
+  const float *x_init;   /* dev [n,P] or NULL: start state replacing 0.5*randn (mask still pinned)        */
+  const float *noise;    /* dev [1+sum_t(1+K_t), n, P] or NULL: injected draws in reference draw order     */
+  uint64_t seed;         /* used when noise == NULL: in-kernel Philox4x32-10 keyed on                      */
+  uint64_t node_offset;  /*   (seed, draw index, node_offset + node) so shards reproduce the global stream */
+} CcspNoise;
+
+const char *ccsp_last_error(void);
+int ccsp_abi_version(void);
+/* Number of kernels launched by this library on the calling thread since the last reset (bench.py's
+ * `gpu_launches`). */
+uint64_t ccsp_launch_count(void);
+void ccsp_reset_launch_count(void);
+
+/* Replaces: ConstraintDiffuser.__init__ + load_state_dict (denoise_fn.py:185-291, ddpm.py:503-514).
+ * Packs the weights into kernel layouts on the current device. Synchronous. */
+int ccsp_model_create(const CcspModelDesc *desc, CcspModel **out);
+void ccsp_model_destroy(CcspModel *m);
+int ccsp_model_set_math(CcspModel *m, int math /* CcspMath */);
+int ccsp_model_get_math(const CcspModel *m);
+
+/* Replaces: the per-call graph handling of ConstraintDiffuser.forward (denoise_fn.py:466-478, 508,
+ * 313-339: re-upload of batch.x / edge_index, per-type `where`, gathers of the run-constant geometry
+ * embeddings).  Inputs are HOST arrays in the reference's batch layout (data_transforms.py:181-200):
+ *   x [n,F] f32, edge_index [2,E] i64, edge_attr [E] f32 (type ids), mask [n] i8.
+ * pose_begin = dims[-1][1]; grasp_begin = dims[1][1] (ignored unless the model has a grasp encoder).
+ * Sorts edges by type, builds the destination-CSR for the deterministic scatter, 1/sqrt(deg), the
+ * pinned rows, and the per-edge static pre-activation (geometry/grasp part of mlps[c] + bias).
+ * Returns after the plan is resident in HBM (synchronises `stream`). */
+int ccsp_plan_create(CcspModel *m, const float *x, int64_t n, int32_t F,
+                     const int64_t *edge_index, const float *edge_attr, const int8_t *mask, int64_t E,
+                     int32_t pose_begin, int32_t grasp_begin, void *stream, CcspPlan **out);
+void ccsp_plan_destroy(CcspPlan *p);
+int64_t ccsp_plan_num_nodes(const CcspPlan *p);
+int64_t ccsp_plan_num_edges(const CcspPlan *p);
+/* padded edge rows actually processed by the edge kernels (multiple of the 128-row tile) */
+int64_t ccsp_plan_num_edge_rows(const CcspPlan *p);
+
+/* Replaces: ConstraintDiffuser.forward(poses_in, batch, t) (denoise_fn.py:453-537), non-energy branch.
+ * poses dev [n,P] -> out dev [n,P]. Asynchronous on `stream`. */
+int ccsp_denoise(CcspPlan *p, const float *poses, int32_t t, float *out, void *stream);
+
+/* Replaces: GaussianDiffusion.p_sample_loop (ddpm.py:260-340) with p_sample (ddpm.py:245-258) and
+ * AnnealedULASampler.sample_step (ddpm.py:955-966).  out dev [n,P]; history dev [T+1,n,P] or NULL
+ * (ddpm.py:323-324, 335-336).  Asynchronous on `stream`. */
+int ccsp_sample(CcspPlan *p, const CcspSchedule *sched, const CcspNoise *noise,
+                float *out, float *history, void *stream);
+
+/* Sampled device timing of the kernels ccsp_sample launches (feeds bench.py's `roofline`): when
+ * stride > 0 every stride-th denoiser evaluation is bracketed by CUDA events recorded on the launch
+ * stream.  ccsp_plan_get_timing synchronises on the recorded events, returns the accumulated
+ * per-kernel times and resets the accumulators. No reference counterpart (the reference only has
+ * wall-clock time.time() around p_sample_loop, ddpm.py:344-349). */
+typedef struct {
+  int64_t samples;      /* evaluations sampled */
+  double ms_edge_l1;    /* first-layer kernel (or the fused edge kernel) */
+  double ms_edge_dec;   /* decoder kernel (0 when fused into the first) */
+  double ms_node;       /* scatter-reduce + update + pose-encoder kernel */
+} CcspTiming;
+int ccsp_plan_set_timing(CcspPlan *p, int32_t stride);
+int ccsp_plan_get_timing(CcspPlan *p, CcspTiming *out);
+/* bytes copied host->device by ccsp_plan_create for this plan (bench.py's e2e.h2d_bytes_per_step) */
+int64_t ccsp_plan_h2d_bytes(const CcspPlan *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CCSP_B200_H_ */

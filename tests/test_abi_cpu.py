@@ -1,0 +1,71 @@
+"""CPU: the C-ABI library builds, loads, and exports every symbol include/ccsp_b200.h declares
+(no compute calls without a GPU), and fails loudly instead of falling back when CUDA is absent."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from diffusion_ccsp_b200 import _abi, build, synthetic
+from diffusion_ccsp_b200.denoise_fn import ConstraintDiffuser
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope='module')
+def lib_path():
+    return build.build_library()
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, 'include', 'ccsp_b200.h')).read()
+    src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+    return sorted(set(re.findall(r'\b(ccsp_[a-z_0-9]+)\s*\(', src)))
+
+
+def test_header_symbols_exported(lib_path):
+    lib = ctypes.CDLL(lib_path)
+    names = declared_symbols()
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(lib, n), f'{n} declared in include/ccsp_b200.h but not exported'
+    assert sorted(_abi.EXPORTS) == names
+    lib.ccsp_abi_version.restype = ctypes.c_int
+    assert lib.ccsp_abi_version() == 1
+
+
+def test_library_is_sm100a_native(lib_path):
+    import subprocess
+    out = subprocess.run(['cuobjdump', '-lelf', lib_path], capture_output=True, text=True).stdout
+    assert 'sm_100a' in out
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason='checks the no-GPU failure mode')
+def test_no_cpu_fallback(lib_path):
+    dims = synthetic.DIMS['qualitative']
+    m = ConstraintDiffuser(dims=dims, input_mode='qualitative', device='cuda', verbose=False)
+    from diffusion_ccsp_b200 import scenes
+    b = scenes.qualitative_batch(2, 4)
+    with pytest.raises(_abi.CcspError):
+        m(torch.zeros(b.num_nodes, 4), b, torch.tensor([3]))
+
+
+def test_state_dict_keys_match_reference_contract():
+    """SURVEY.md §8b checkpoint key contract."""
+    from diffusion_ccsp_b200.ddpm import GaussianDiffusion
+    for mode, tri in (('qualitative', False), ('diffuse_pairwise', False), ('diffuse_pairwise', True), ('robot_box', False)):
+        dims = synthetic.dims_for(mode, tri)
+        m = ConstraintDiffuser(dims=dims, input_mode=mode, device='cuda', verbose=False)
+        gd = GaussianDiffusion(m, timesteps=10, EBM='ULA')
+        keys = set(gd.state_dict().keys())
+        sd = synthetic.make_state_dict(dims, mode)
+        assert set(sd.keys()) <= keys
+        sched = {'betas', 'alphas_cumprod', 'alphas_cumprod_prev', 'sqrt_alphas_cumprod',
+                 'sqrt_one_minus_alphas_cumprod', 'log_one_minus_alphas_cumprod', 'sqrt_recip_alphas_cumprod',
+                 'sqrt_recipm1_alphas_cumprod', 'posterior_variance', 'posterior_log_variance_clipped',
+                 'posterior_mean_coef1', 'posterior_mean_coef2'}
+        assert keys == sched | set(sd.keys())
+        for k, v in sd.items():
+            assert gd.state_dict()[k].shape == v.shape, k
+        gd.load_state_dict(sd, strict=False)

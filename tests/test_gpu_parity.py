@@ -1,0 +1,203 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via the reference-shaped Python classes) against
+  (1) the committed golden vectors produced by the UNMODIFIED reference (tests/golden/*.npz), and
+  (2) the numpy oracle (oracle/ccsp_oracle.py) on seeded inputs, incl. ragged / empty / degenerate graphs.
+
+Parity measure: max|a-b| / max(1, max|ref|).
+Stated FP32 tolerances for math='fp32' (FP32 FMA; differs from the reference only in summation order):
+    single denoiser evaluation  5e-6,   trajectories (T<=100, |x| up to 1.6e4)  2e-5.
+"""
+import numpy as np
+import pytest
+import torch
+
+from diffusion_ccsp_b200 import scenes, synthetic
+from diffusion_ccsp_b200.ddpm import GaussianDiffusion
+from diffusion_ccsp_b200.denoise_fn import ConstraintDiffuser
+from oracle import ccsp_oracle as orc
+from tests.util import case_model, golden_names, load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = {'fp32': dict(fwd=5e-6, traj=2e-5)}
+MATHS = ['fp32']
+
+
+def build(mode, dims, sd, T=100, EBM='ULA', K=10, math='fp32'):
+    m = ConstraintDiffuser(dims=dims, input_mode=mode, device='cuda', verbose=False, math=math)
+    gd = GaussianDiffusion(m, timesteps=T, EBM=EBM, samples_per_step=K).eval()
+    missing, unexpected = gd.load_state_dict(sd, strict=False)
+    assert not unexpected
+    return m, gd
+
+
+def np_sd(sd):
+    return {k: v.numpy() for k, v in sd.items()}
+
+
+# ---------------------------------------------------------------------------------------------------
+# golden vectors from the unmodified reference
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('math', MATHS)
+@pytest.mark.parametrize('name', golden_names('forward_'))
+def test_forward_vs_reference_golden(name, math):
+    z, batch = load_golden(name)
+    mode, dims, sd = case_model(z)
+    m, _ = build(mode, dims, sd, math=math)
+    for t, ref in zip(z['t'], z['out']):
+        out = m(torch.from_numpy(z['poses_in']), batch, torch.tensor([int(t)]), eval=True).cpu().numpy()
+        assert rel_err(out, ref) < TOL[math]['fwd'], (name, t, rel_err(out, ref))
+        mk = batch.mask.numpy().astype(bool)
+        assert np.array_equal(out[mk], batch.x.numpy()[:, -dims[-1][0]:][mk])     # denoise_fn.py:533, bit-exact
+
+
+@pytest.mark.parametrize('math', MATHS)
+@pytest.mark.parametrize('name', golden_names('traj_'))
+def test_trajectory_vs_reference_golden(name, math):
+    z, batch = load_golden(name)
+    mode, dims, sd = case_model(z)
+    T, K = int(z['T']), int(z['K'])
+    _, gd = build(mode, dims, sd, T=T, EBM='ULA' if K else False, K=K if K else 10, math=math)
+    noise = synthetic.make_noise(T, K, batch.num_nodes, dims[-1][0], seed=int(z['noise_seed']))
+    out, hist = gd.sample(batch, return_history=True, noise=noise)
+    assert len(hist) == T + 1                                                      # ddpm.py:323-336
+    out = out.cpu().numpy()
+    hist = torch.stack(hist).cpu().numpy()
+    assert rel_err(out, z['out']) < TOL[math]['traj'], (name, rel_err(out, z['out']))
+    assert rel_err(hist, z['history']) < TOL[math]['traj'], (name, rel_err(hist, z['history']))
+    mk = batch.mask.numpy().astype(bool)
+    gt = batch.x.numpy()[:, dims[-1][1]:dims[-1][2]]
+    assert all(np.array_equal(h[mk], gt[mk]) for h in hist)                        # pinned rows, every timestep
+    assert len(gd.sample_loop_time) == 1
+
+
+# ---------------------------------------------------------------------------------------------------
+# oracle comparisons on graphs the goldens do not cover
+# ---------------------------------------------------------------------------------------------------
+def oracle_forward(sd, dims, mode, batch, poses, t):
+    return orc.OracleDenoiser(np_sd(sd), dims, mode).forward(poses, batch, t)
+
+
+@pytest.mark.parametrize('math', MATHS)
+@pytest.mark.parametrize('seed', [0, 1, 2])
+def test_random_typed_graphs_vs_oracle(seed, math):
+    """ragged scenes, types with zero edges, multi-edges, both argument orders."""
+    rng = np.random.default_rng(seed)
+    mode, dims = 'qualitative', synthetic.DIMS['qualitative']
+    sd = synthetic.make_state_dict(dims, mode, seed=seed)
+    parts = [scenes.random_typed_scene(rng, int(rng.integers(1, 10)), 13 if seed else 5, int(rng.integers(0, 60)), 6)
+             for _ in range(int(rng.integers(1, 12)))]
+    batch = scenes.collate(parts)
+    m, _ = build(mode, dims, sd, math=math)
+    poses = rng.standard_normal((batch.num_nodes, 4)).astype(np.float32)
+    for t in (0, 13, 99):
+        ref = oracle_forward(sd, dims, mode, batch, poses, t)
+        out = m(torch.from_numpy(poses), batch, torch.tensor([t])).cpu().numpy()
+        assert rel_err(out, ref) < TOL[math]['fwd'], rel_err(out, ref)
+
+
+@pytest.mark.parametrize('math', MATHS)
+def test_isolated_node_is_nan_like_reference(math):
+    """0/sqrt(0) for a node without incident edges (denoise_fn.py:524)."""
+    rng = np.random.default_rng(5)
+    mode, dims = 'diffuse_pairwise', synthetic.DIMS['diffuse_pairwise']
+    sd = synthetic.make_state_dict(dims, mode, seed=5)
+    x = rng.uniform(-1, 1, (4, 4)).astype(np.float32)
+    batch = scenes.SceneBatch(x, np.array([[1], [0]]), np.array([0.0]), np.array([1, 0, 0, 0], np.int8))
+    poses = rng.standard_normal((4, 2)).astype(np.float32)
+    ref = oracle_forward(sd, dims, mode, batch, poses, 7)
+    m, _ = build(mode, dims, sd, math=math)
+    out = m(torch.from_numpy(poses), batch, torch.tensor([7])).cpu().numpy()
+    assert np.isnan(ref[2:]).all() and np.isnan(out[2:]).all()
+    assert rel_err(out[:2], ref[:2]) < TOL[math]['fwd']
+
+
+@pytest.mark.parametrize('math', MATHS)
+def test_empty_edge_set_and_unknown_types(math):
+    """no edges at all -> every free node NaN, pinned node = x[:, -P:]; type ids outside the vocabulary are
+    ignored (denoise_fn.py:317 `edge_attr == i` never matches)."""
+    mode, dims = 'diffuse_pairwise', synthetic.DIMS['diffuse_pairwise']
+    sd = synthetic.make_state_dict(dims, mode, seed=6)
+    rng = np.random.default_rng(6)
+    x = rng.uniform(-1, 1, (3, 4)).astype(np.float32)
+    m, _ = build(mode, dims, sd, math=math)
+    poses = rng.standard_normal((3, 2)).astype(np.float32)
+    b0 = scenes.SceneBatch(x, np.zeros((2, 0), np.int64), np.zeros((0,), np.float32), np.array([1, 0, 0], np.int8))
+    out = m(torch.from_numpy(poses), b0, torch.tensor([3])).cpu().numpy()
+    assert np.array_equal(out[0], x[0, -2:]) and np.isnan(out[1:]).all()
+    b1 = scenes.SceneBatch(x, np.array([[1, 2, 1], [0, 0, 2]]), np.array([0.0, 7.0, 1.0]), np.array([1, 0, 0], np.int8))
+    ref = oracle_forward(sd, dims, mode, b1, poses, 3)
+    out = m(torch.from_numpy(poses), b1, torch.tensor([3])).cpu().numpy()
+    assert rel_err(out, ref) < TOL[math]['fwd']
+
+
+@pytest.mark.parametrize('math', MATHS)
+def test_edge_and_scene_permutation_invariance(math):
+    """per-scene results do not depend on edge order or on where the scene sits in the batch."""
+    mode, dims = 'qualitative', synthetic.DIMS['qualitative']
+    sd = synthetic.make_state_dict(dims, mode, seed=9)
+    batch = scenes.qualitative_batch(6, 6)
+    rng = np.random.default_rng(9)
+    perm = rng.permutation(batch.num_edges)
+    b_perm = scenes.SceneBatch(batch.x, batch.edge_index[:, perm], batch.edge_attr[perm], batch.mask)
+    order = rng.permutation(6)
+    b_scn = scenes.take_scenes(batch, order)
+    _, gd = build(mode, dims, sd, T=4, K=3, math=math)
+    n, P = batch.num_nodes, 4
+    noise = synthetic.make_noise(4, 3, n, P, seed=1)
+    base = gd.sample(batch, noise=noise).cpu().numpy()
+    out_perm = gd.sample(b_perm, noise=noise).cpu().numpy()
+    assert rel_err(out_perm, base) < TOL[math]['traj']
+    off = batch.scene_node_ranges()
+    node_perm = np.concatenate([np.arange(off[s], off[s + 1]) for s in order])
+    out_scn = gd.sample(b_scn, noise=noise[:, node_perm]).cpu().numpy()
+    assert rel_err(out_scn, base[node_perm]) < TOL[math]['traj']
+
+
+# ---------------------------------------------------------------------------------------------------
+# full-size workload (BASELINE.json configs[1]: qualitative N=8, batch 1024)
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('math', MATHS)
+def test_config2_full_batch_forward_and_short_trajectory(math):
+    mode, dims = 'qualitative', synthetic.DIMS['qualitative']
+    sd = synthetic.make_state_dict(dims, mode, seed=0)
+    batch = scenes.qualitative_batch(1024, 8)
+    assert batch.num_nodes == 9216 and 79000 < batch.num_edges < 83000
+    m, gd = build(mode, dims, sd, T=2, K=2, math=math)
+    rng = np.random.default_rng(3)
+    poses = rng.standard_normal((batch.num_nodes, 4)).astype(np.float32)
+    ref = oracle_forward(sd, dims, mode, batch, poses, 1)
+    out = m(torch.from_numpy(poses), batch, torch.tensor([1])).cpu().numpy()
+    assert rel_err(out, ref) < TOL[math]['fwd'], rel_err(out, ref)
+    noise = synthetic.make_noise(2, 2, batch.num_nodes, 4, seed=8)
+    o = orc.OracleDiffusion(orc.OracleDenoiser(np_sd(sd), dims, mode), 2, 'ULA', 2).p_sample_loop(batch, noise.numpy())
+    out = gd.sample(batch, noise=noise).cpu().numpy()
+    assert rel_err(out, o) < TOL[math]['traj'], rel_err(out, o)
+
+
+# ---------------------------------------------------------------------------------------------------
+# in-kernel Philox stream
+# ---------------------------------------------------------------------------------------------------
+def test_philox_deterministic_and_shard_invariant():
+    mode, dims = 'qualitative', synthetic.DIMS['qualitative']
+    sd = synthetic.make_state_dict(dims, mode, seed=0)
+    batch = scenes.qualitative_batch(8, 4)
+    _, gd = build(mode, dims, sd, T=3, K=2)
+    a, hist = gd.sample(batch, seed=1234, return_history=True)
+    b = gd.sample(batch, seed=1234)
+    c = gd.sample(batch, seed=1235)
+    assert torch.equal(a, b) and not torch.equal(a, c)
+    # x_T = 0.5 * z on free rows: mean 0, std 0.5
+    big = scenes.qualitative_batch(1024, 8)
+    _, gd1 = build(mode, dims, sd, T=1, K=0, EBM=False)
+    _, h = gd1.sample(big, seed=7, return_history=True)
+    free = ~big.mask.bool()
+    x0 = h[0].cpu()[free]
+    assert abs(float(x0.mean())) < 0.02 and abs(float(x0.std()) - 0.5) < 0.02
+    assert abs(float((x0 / 0.5).pow(4).mean()) - 3.0) < 0.2          # Gaussian kurtosis
+    # sharding: two half-batches with node_offset reproduce the full-batch stream bit-for-bit
+    off = batch.scene_node_ranges()
+    parts = []
+    for lo, hi in ((0, 4), (4, 8)):
+        sub = batch.select_scenes(lo, hi)
+        parts.append(gd.sample(sub, seed=1234, node_offset=int(off[lo])))
+    assert torch.equal(torch.cat(parts), a)
