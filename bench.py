@@ -317,7 +317,7 @@ def run_ours(args):
 
 
 def default_math():
-    return 'fp32'
+    return 'bf16x3'
 
 
 if __name__ == '__main__':

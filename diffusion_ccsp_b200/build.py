@@ -36,7 +36,8 @@ def _nvcc() -> str:
 
 def _sources():
     srcs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith('.cu')]
-    deps = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))] + [os.path.join(ROOT, 'include', 'ccsp_b200.h')]
+    deps = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if os.path.isfile(os.path.join(CSRC, f))]
+    deps.append(os.path.join(ROOT, 'include', 'ccsp_b200.h'))
     return srcs, deps
 
 
@@ -70,6 +71,21 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_tc_test() -> str:
+    """Standalone numerics/throughput harness for the tcgen05 GEMM kernels (csrc/tests/tc_gemm_test.cu)."""
+    src = os.path.join(CSRC, 'tests', 'tc_gemm_test.cu')
+    out = os.path.join(LIBDIR, 'tc_gemm_test')
+    os.makedirs(LIBDIR, exist_ok=True)
+    cmd = [_nvcc(), '-O3', '-std=c++17', '-lineinfo', '-gencode', 'arch=compute_100a,code=sm_100a', '-o', out, src]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError('nvcc failed for tc_gemm_test')
+    return out
+
+
 if __name__ == '__main__':
     path = build_library(force='--force' in sys.argv, verbose=True)
     print('built', path)
+    if '--tests' in sys.argv:
+        print('built', build_tc_test())

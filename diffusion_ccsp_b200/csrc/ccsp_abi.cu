@@ -9,6 +9,7 @@
 
 #include "common.cuh"
 #include "kernels_simt.cuh"
+#include "kernels_tc.cuh"
 
 namespace ccsp {
 static thread_local std::string g_last_error;
@@ -96,6 +97,12 @@ struct CcspModel {
   float *bias = nullptr;          // [C][512]
   float *tb = nullptr;            // [tb_T][C][512] per-(t, type) time term
   int tb_T = 0;
+  // tensor-core operand blobs (kernels_tc.cuh), packed lazily per CcspMath mode
+  int num_sms = 148;
+  std::vector<float> h_pose_w;    // [C][512][512] pose columns of mlps[c].weight, reference [out][k] layout
+  std::vector<float> h_dec_w1;    // [128][256]
+  uint8_t *blob_l1[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  uint8_t *blob_dec[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 struct CcspPlan {
@@ -148,6 +155,7 @@ static int model_build(CcspModel *m, const CcspModelDesc *d) {
 
   std::vector<float> h;
   CCSP_CUDA_TRY(fetch(d->dec_w0, (size_t)CCSP_HH * CCSP_H, h));
+  m->h_dec_w1 = h;
   CCSP_CUDA_TRY(upload(m->pool, &m->dec_w1t, transpose_cols(h, CCSP_HH, CCSP_H, 0, CCSP_H)));
   CCSP_CUDA_TRY(fetch(d->dec_b0, CCSP_HH, h));
   CCSP_CUDA_TRY(upload(m->pool, &m->dec_b1, h));
@@ -174,8 +182,16 @@ static int model_build(CcspModel *m, const CcspModelDesc *d) {
   const int Ks = m->nseg_static * CCSP_H, Kin = Ks + 3 * CCSP_H;
   std::vector<float> wst((size_t)m->C * Ks * CCSP_H2), wpt((size_t)m->C * CCSP_H2 * CCSP_H2),
       wtt((size_t)m->C * CCSP_H * CCSP_H2), bias((size_t)m->C * CCSP_H2);
+  m->h_pose_w.resize((size_t)m->C * CCSP_H2 * CCSP_H2);
+  {
+    cudaDeviceProp prop;
+    CCSP_CUDA_TRY(cudaGetDeviceProperties(&prop, m->device));
+    m->num_sms = prop.multiProcessorCount;
+  }
   for (int c = 0; c < m->C; ++c) {
     CCSP_CUDA_TRY(fetch(d->mlp_w[c], (size_t)CCSP_H2 * Kin, h));
+    for (int r = 0; r < CCSP_H2; ++r)
+      std::memcpy(&m->h_pose_w[((size_t)c * CCSP_H2 + r) * CCSP_H2], &h[(size_t)r * Kin + Ks], CCSP_H2 * sizeof(float));
     auto a = transpose_cols(h, CCSP_H2, Kin, 0, Ks);
     auto b = transpose_cols(h, CCSP_H2, Kin, Ks, Ks + CCSP_H2);
     auto t = transpose_cols(h, CCSP_H2, Kin, Ks + CCSP_H2, Kin);
@@ -209,6 +225,60 @@ static int ensure_time_table(CcspModel *m, int T, cudaStream_t st) {
   return CCSP_OK;
 }
 
+// ---- tensor-core modes -----------------------------------------------------------------------------
+template <int KIND, int NSPLIT> using L1Cfg = tc::Cfg<KIND, NSPLIT, 256, tc::EPI_TC_L1>;
+template <int KIND, int NSPLIT> using DecCfg = tc::Cfg<KIND, NSPLIT, 128, tc::EPI_TC_DEC>;
+
+template <int KIND, int NSPLIT>
+static int pack_tc_blobs(CcspModel *m, int math) {
+  using L1 = L1Cfg<KIND, NSPLIT>;
+  using Dec = DecCfg<KIND, NSPLIT>;
+  const size_t per = (size_t)2 * (CCSP_H2 / L1::KC) * L1::B_STAGE;
+  std::vector<uint8_t> b1(per * m->C);
+  for (int c = 0; c < m->C; ++c)
+    tc::pack_b_blob<L1>(&m->h_pose_w[(size_t)c * CCSP_H2 * CCSP_H2], CCSP_H2, 0, CCSP_H2, CCSP_H2, b1.data() + c * per);
+  std::vector<uint8_t> b2((size_t)(CCSP_H / Dec::KC) * Dec::B_STAGE);
+  tc::pack_b_blob<Dec>(m->h_dec_w1.data(), CCSP_H, 0, CCSP_H, CCSP_HH, b2.data());
+  CCSP_CUDA_TRY(upload(m->pool, &m->blob_l1[math], b1));
+  CCSP_CUDA_TRY(upload(m->pool, &m->blob_dec[math], b2));
+  return CCSP_OK;
+}
+
+static int ensure_tc_blobs(CcspModel *m, int math) {
+  if (math == CCSP_MATH_FP32 || m->blob_l1[math]) return CCSP_OK;
+  switch (math) {
+    case CCSP_MATH_TF32X3: return pack_tc_blobs<tc::KIND_TF32, 3>(m, math);
+    case CCSP_MATH_BF16X3: return pack_tc_blobs<tc::KIND_BF16, 3>(m, math);
+    case CCSP_MATH_TF32: return pack_tc_blobs<tc::KIND_TF32, 1>(m, math);
+    case CCSP_MATH_BF16: return pack_tc_blobs<tc::KIND_BF16, 1>(m, math);
+  }
+  set_error("unknown math mode");
+  return CCSP_ERR_INVALID;
+}
+
+template <int KIND, int NSPLIT>
+static int launch_edge_tc(CcspPlan *p, const float *tb, cudaStream_t st, cudaEvent_t mid) {
+  CcspModel *m = p->m;
+  tc::GemmArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.a_src[0] = p->pe; a.a_src[1] = p->pe; a.a_idx[0] = p->src_i; a.a_idx[1] = p->src_j; a.nseg = 2;
+  a.b_blob = m->blob_l1[m->math]; a.tile_type = p->tile_type;
+  a.num_m_tiles = (int)(p->Epad / CCSP_TILE_M); a.n_tiles = 2;
+  a.S = p->S; a.tb = tb; a.H = p->H;
+  CCSP_CUDA_TRY((tc::launch_gemm_tc<L1Cfg<KIND, NSPLIT>>(a, m->num_sms, st)));
+  count_launch();
+  if (mid) CCSP_CUDA_TRY(cudaEventRecord(mid, st));
+  tc::GemmArgs d;
+  std::memset(&d, 0, sizeof(d));
+  d.a_src[0] = p->H; d.nseg = 1;
+  d.b_blob = m->blob_dec[m->math];
+  d.num_m_tiles = (int)(2 * p->Epad / CCSP_TILE_M); d.n_tiles = 1;
+  d.bd1 = m->dec_b1; d.Wd2 = m->dec_w2; d.bd2 = m->dec_b2; d.P = m->P; d.o = p->o;
+  CCSP_CUDA_TRY((tc::launch_gemm_tc<DecCfg<KIND, NSPLIT>>(d, m->num_sms, st)));
+  count_launch();
+  return CCSP_OK;
+}
+
 // one evaluation of the two dense per-edge layers for timestep t: pe -> H -> o
 static int launch_edge(CcspPlan *p, int t, cudaStream_t st, cudaEvent_t mid = nullptr) {
   CcspModel *m = p->m;
@@ -230,8 +300,12 @@ static int launch_edge(CcspPlan *p, int t, cudaStream_t st, cudaEvent_t mid = nu
       CCSP_LAUNCH_CHECK();
       return CCSP_OK;
     }
+    case CCSP_MATH_TF32X3: return launch_edge_tc<tc::KIND_TF32, 3>(p, tb, st, mid);
+    case CCSP_MATH_BF16X3: return launch_edge_tc<tc::KIND_BF16, 3>(p, tb, st, mid);
+    case CCSP_MATH_TF32: return launch_edge_tc<tc::KIND_TF32, 1>(p, tb, st, mid);
+    case CCSP_MATH_BF16: return launch_edge_tc<tc::KIND_BF16, 1>(p, tb, st, mid);
     default:
-      set_error("math mode not available in this build");
+      set_error("unknown math mode");
       return CCSP_ERR_STATE;
   }
 }
@@ -292,7 +366,10 @@ void ccsp_model_destroy(CcspModel *m) {
 
 int ccsp_model_set_math(CcspModel *m, int math) {
   CCSP_REQUIRE(m, "null model");
-  CCSP_REQUIRE(math == CCSP_MATH_FP32, "math mode not available in this build");
+  CCSP_REQUIRE(math >= CCSP_MATH_FP32 && math <= CCSP_MATH_BF16, "unknown math mode");
+  CCSP_CUDA_TRY(cudaSetDevice(m->device));
+  int rc = ensure_tc_blobs(m, math);
+  if (rc) return rc;
   m->math = math;
   return CCSP_OK;
 }
@@ -303,7 +380,7 @@ int ccsp_plan_create(CcspModel *m, const float *x, int64_t n, int32_t F, const i
                      const float *edge_attr, const int8_t *mask, int64_t E, int32_t pose_begin,
                      int32_t grasp_begin, void *stream, CcspPlan **out) {
   CCSP_REQUIRE(m && x && mask && out, "null argument");
-  CCSP_REQUIRE(n > 0 && n < (1ll << 30) && E >= 0 && E < (1ll << 29), "n/E out of range");
+  CCSP_REQUIRE(n > 0 && n < (1ll << 23) && E >= 0 && E < (1ll << 22), "n/E out of range (32-bit row offsets)");
   CCSP_REQUIRE(E == 0 || (edge_index && edge_attr), "null edge arrays");
   const int P = m->P, G = m->G, C = m->C;
   CCSP_REQUIRE(F >= G && pose_begin >= 0 && pose_begin + P <= F, "feature slices exceed row width");
