@@ -7,7 +7,7 @@
 #define CCSP_H 256            // hidden_dim
 #define CCSP_H2 512           // 2 * hidden_dim (first-layer output width, one half per edge endpoint)
 #define CCSP_HH 128           // hidden_dim / 2
-#define CCSP_TILE_M 128       // edge rows per tile (padded per constraint type)
+#define CCSP_TILE_M 256       // edge rows per tile (padded per constraint type)
 #define CCSP_MAXP 8
 
 namespace ccsp {

@@ -1,14 +1,14 @@
 // kernels_tc.cuh — tcgen05 (5th-gen tensor core) kernels for the two dense per-edge layers.
 //
-// One persistent, warp-specialised GEMM kernel template, C[128 x NTILE] tiles with FP32 accumulators in
+// One persistent, warp-specialised GEMM kernel template, C[256 x NTILE] tiles with FP32 accumulators in
 // TMEM, operands staged in shared memory in the canonical K-major SWIZZLE_64B layout:
 //
-//   warps 0-3  epilogue   tcgen05.ld accumulator -> registers -> fused epilogue -> global
-//   warps 4-7  A producer gather pose-embedding rows through the edge index (coalesced 16 B loads from
-//                         L2), split FP32 -> (hi, lo) operand pair, st.shared into the swizzled layout
-//   warp  8    B loader   weights are pre-split / pre-swizzled per k-chunk on the host, one
-//                         cp.async.bulk (TMA engine, no tensor map needed) per stage
-//   warp  9    MMA issuer tcgen05.mma (one elected lane), tcgen05.commit -> mbarriers; owns TMEM alloc
+//   warps 0-7   epilogue   tcgen05.ld accumulator -> registers -> fused epilogue -> global
+//   warps 8-11  A producer gather pose-embedding rows through the edge index (16 B loads from L2),
+//                          split FP32 -> (hi, lo) operand pair, st.shared into the swizzled layout
+//   warp  12    B loader   weights are pre-split / pre-swizzled per k-chunk on the host, one
+//                          cp.async.bulk (TMA engine, no tensor map needed) per stage
+//   warp  13    MMA issuer tcgen05.mma (one elected lane), tcgen05.commit -> mbarriers; owns TMEM alloc
 //
 // FP32 fidelity: the reference computes these layers in true FP32 (cuBLAS/oneDNN sgemm).  The tensor
 // cores take TF32/BF16 operands, so every FP32 operand x is split as x = hi + lo (+ residual) and
@@ -27,9 +27,10 @@ enum { KIND_TF32 = 0, KIND_BF16 = 1 };
 enum { EPI_TC_L1 = 0, EPI_TC_DEC = 1 };
 
 constexpr int ROWB = 64;        // bytes of K per operand row per stage (SWIZZLE_64B span)
-constexpr int NSTAGE = 4;       // smem ring depth == number of A-producer warps
-constexpr int TILE_M = 128;
-constexpr int NUM_THREADS = 320;
+constexpr int SUB_M = 128;      // rows per tcgen05.mma (one TMEM accumulator = 128 lanes)
+constexpr int NUM_EPI_WARPS = 8, NUM_PROD_WARPS = 4;
+constexpr int WARP_PROD0 = NUM_EPI_WARPS, WARP_BLOAD = WARP_PROD0 + NUM_PROD_WARPS, WARP_MMA = WARP_BLOAD + 1;
+constexpr int NUM_THREADS = (WARP_MMA + 1) * 32;   // 448
 constexpr uint32_t SPIN_LIMIT = 1u << 27;   // bounded spin: a protocol bug traps instead of hanging the GPU
 
 // ---------------------------------------------------------------------------------------------------
@@ -145,6 +146,10 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Tile shape: one CTA tile = 256 operand rows (two 128-row sub-tiles = two TMEM accumulators) x NTILE
+// output columns.  Both sub-tiles share every B (weight) stage, which halves the L2->SM weight traffic
+// per FLOP relative to a 128-row tile — the resource that bounds this kernel.
+// ---------------------------------------------------------------------------------------------------
 template <int KIND_, int NSPLIT_, int NTILE_, int EPI_>
 struct Cfg {
   static constexpr int KIND = KIND_, NSPLIT = NSPLIT_, NTILE = NTILE_, EPI = EPI_;
@@ -153,16 +158,23 @@ struct Cfg {
   static constexpr int UMMA_K = 32 / ELT;                    // K per tcgen05.mma (8 / 16)
   static constexpr int KSTEPS = KC / UMMA_K;                 // 2
   static constexpr int NS = NSPLIT == 3 ? 2 : 1;             // operand copies per stage (hi[, lo])
-  static constexpr int A_PART = TILE_M * ROWB;               // 8 KB
+  static constexpr int SUB = 2;                              // 128-row sub-tiles per CTA tile
+  static constexpr int TILE_ROWS = SUB * SUB_M;              // 256
+  static constexpr int A_PART = SUB_M * ROWB;                // 8 KB
+  static constexpr int A_SUB = NS * A_PART;
+  static constexpr int A_STAGE = SUB * A_SUB;
   static constexpr int B_PART = NTILE * ROWB;
-  static constexpr int A_STAGE = NS * A_PART;
   static constexpr int B_STAGE = NS * B_PART;
   static constexpr int STAGE = A_STAGE + B_STAGE;
-  static constexpr int TMEM_COLS = 2 * NTILE;                // double-buffered accumulator
+  static constexpr int NSTAGE = STAGE <= 48 * 1024 ? 4 : 3;  // smem ring depth
+  static constexpr int ACC_COLS = SUB * NTILE;               // TMEM columns per tile
+  static constexpr int NBUF = 512 / ACC_COLS;                // accumulator buffers (1 or 2)
+  static constexpr int TMEM_COLS = 512;
   static constexpr int SMEM_EXTRA = 8192;                    // barriers, tmem ptr, epilogue constants
   static constexpr int SMEM_BYTES = NSTAGE * STAGE + SMEM_EXTRA + 1024;   // + alignment slack
   static constexpr uint32_t IDESC = (1u << 4) | ((KIND == KIND_TF32 ? 2u : 1u) << 7) | ((KIND == KIND_TF32 ? 2u : 1u) << 10) |
-                                    ((uint32_t)(NTILE >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+                                    ((uint32_t)(NTILE >> 3) << 17) | ((uint32_t)(SUB_M >> 4) << 24);
+  static_assert(NBUF >= 1 && SMEM_BYTES <= 227 * 1024, "tile does not fit");
 };
 
 struct GemmArgs {
@@ -172,8 +184,8 @@ struct GemmArgs {
   int nseg;
   // B operand: host-packed stage blobs [group][n_tile][k-chunk][B_STAGE bytes]
   const uint8_t *b_blob;
-  const int *tile_type;      // weight group per 128-row tile (nullptr -> group 0)
-  int num_m_tiles, n_tiles;
+  const int *tile_type;      // weight group per 256-row tile (nullptr -> group 0)
+  int num_m_tiles, n_tiles;  // 256-row tiles, NTILE-column tiles
   // EPI_TC_L1: H[row, nt*NTILE + j] = SiLU(acc + S[row, .] + tb[group, .])
   const float *S, *tb;
   float *H;
@@ -181,118 +193,138 @@ struct GemmArgs {
   const float *bd1, *Wd2, *bd2;
   int P;
   float *o;
+  // performance ablations for the harness (results are garbage when non-zero):
+  //   1 = producers skip the gather/convert/store, 2 = B loader skips the bulk copy,
+  //   4 = epilogue skips global loads/stores, 8 = MMA warp skips the tcgen05.mma instructions
+  int dbg;
 };
 
 template <class C>
 __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const GemmArgs A) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t *extra = smem + NSTAGE * C::STAGE;
+  uint8_t *extra = smem + C::NSTAGE * C::STAGE;
   uint64_t *full_bar = reinterpret_cast<uint64_t *>(extra);            // [NSTAGE]
-  uint64_t *empty_bar = full_bar + NSTAGE;                             // [NSTAGE]
-  uint64_t *tfull_bar = empty_bar + NSTAGE;                            // [2]
-  uint64_t *tempty_bar = tfull_bar + 2;                                // [2]
+  uint64_t *empty_bar = full_bar + 4;                                  // [NSTAGE]
+  uint64_t *tfull_bar = empty_bar + 4;                                 // [NBUF]
+  uint64_t *tempty_bar = tfull_bar + 2;                                // [NBUF]
   uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(tempty_bar + 2);
-  float *epi_const = reinterpret_cast<float *>(extra + 256);           // L1: tb slice [NTILE]; DEC: bd1[128] + Wd2[P*128] + bd2[P]
+  float *epi_const = reinterpret_cast<float *>(extra + 256);           // L1: tb slice [NTILE]; DEC: bd1[128] + w2t[128*8] + bd2[8]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int NKC = A.nseg * CCSP_H / C::KC;
   const int num_tiles = A.num_m_tiles * A.n_tiles;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full_bar[s], 32 + 1); mbar_init(&empty_bar[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 128); }
+    for (int s = 0; s < C::NSTAGE; ++s) { mbar_init(&full_bar[s], 32 + 1); mbar_init(&empty_bar[s], 1); }
+    for (int b = 0; b < C::NBUF; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], NUM_EPI_WARPS * 32); }
     fence_barrier_init();
   }
-  if (warp == 9) tmem_alloc(tmem_ptr, C::TMEM_COLS);
-  if (C::EPI == EPI_TC_DEC && warp < 4) {
-    for (int i = threadIdx.x; i < CCSP_HH; i += 128) epi_const[i] = A.bd1[i];
-    for (int i = threadIdx.x; i < CCSP_MAXP * CCSP_HH; i += 128) {      // w2t[j][p], zero-padded to 8 outputs
+  if (warp == WARP_MMA) tmem_alloc(tmem_ptr, C::TMEM_COLS);
+  if (C::EPI == EPI_TC_DEC && warp < NUM_EPI_WARPS) {
+    const int nth = NUM_EPI_WARPS * 32;
+    for (int i = threadIdx.x; i < CCSP_HH; i += nth) epi_const[i] = A.bd1[i];
+    for (int i = threadIdx.x; i < CCSP_MAXP * CCSP_HH; i += nth) {      // w2t[j][p], zero-padded to 8 outputs
       const int j = i / CCSP_MAXP, pp = i % CCSP_MAXP;
       epi_const[CCSP_HH + i] = pp < A.P ? A.Wd2[pp * CCSP_HH + j] : 0.f;
     }
-    for (int i = threadIdx.x; i < CCSP_MAXP; i += 128) epi_const[CCSP_HH + CCSP_MAXP * CCSP_HH + i] = i < A.P ? A.bd2[i] : 0.f;
+    for (int i = threadIdx.x; i < CCSP_MAXP; i += nth) epi_const[CCSP_HH + CCSP_MAXP * CCSP_HH + i] = i < A.P ? A.bd2[i] : 0.f;
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  if (warp >= 4 && warp < 8) {
-    // ================================ A producers: warp w owns ring stage w ====================
-    const int w = warp - 4;
-    const uint32_t stA = smem_u32(smem + w * C::STAGE);
+  if (warp >= WARP_PROD0 && warp < WARP_PROD0 + C::NSTAGE) {
+    // ================================ A producers ================================================
+    // producer warp pw OWNS ring stage pw and converts k-chunks kc == pw (mod NSTAGE): 256 rows x 64 B of
+    // operand per chunk.  One owner per stage keeps every waiter at most one mbarrier phase ahead (parity
+    // waits cannot tell phases two apart); with a 3-deep ring the 4th producer warp stays idle.
+    const int pw = warp - WARP_PROD0;
+    const uint32_t smem_base = smem_u32(smem);
     const int q = lane & 3, r0 = lane >> 2;
-    uint32_t uses = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile / A.n_tiles) * TILE_M;
+    uint32_t tile_iter = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_iter) {
+      const int m0 = (tile / A.n_tiles) * C::TILE_ROWS;
       int cur_seg = -1;
-      uint32_t rowoff[16];
-      for (int kc = w; kc < NKC; kc += NSTAGE) {
+      uint32_t rowoff[32];
+      const int kc_first = (pw + C::NSTAGE - (int)((tile_iter * (uint32_t)NKC) % C::NSTAGE)) % C::NSTAGE;
+      for (int kc = kc_first; kc < NKC; kc += C::NSTAGE) {
+        const uint32_t g = tile_iter * NKC + kc;             // global chunk counter; g % NSTAGE == pw
+        const uint32_t s = pw;
         const int k0 = kc * C::KC;
         const int seg = k0 >> 8;
         if (seg != cur_seg) {
           cur_seg = seg;
 #pragma unroll
-          for (int p = 0; p < 16; ++p) {
+          for (int p = 0; p < 32; ++p) {
             const int row = m0 + p * 8 + r0;
             rowoff[p] = (uint32_t)(A.a_idx[seg] ? __ldg(&A.a_idx[seg][row]) : row) * CCSP_H;
           }
         }
         const float *src = A.a_src[seg] + (k0 & (CCSP_H - 1));
-        mbar_wait(&empty_bar[w], (uses & 1) ^ 1);
+        const uint32_t stA = smem_base + s * C::STAGE;
+        mbar_wait(&empty_bar[s], ((g / C::NSTAGE) & 1) ^ 1);
+        if (A.dbg & 1) {
+          mbar_arrive(&full_bar[s]);
+          continue;
+        }
         if (C::KIND == KIND_TF32) {
-          float4 v[16];
 #pragma unroll
-          for (int p = 0; p < 16; ++p) v[p] = __ldg(reinterpret_cast<const float4 *>(src + rowoff[p] + q * 4));
+          for (int hb = 0; hb < 2; ++hb) {                 // two batches of 16 rows-in-flight per lane
+            float4 v[16];
 #pragma unroll
-          for (int p = 0; p < 16; ++p) {
-            const uint32_t off = sw64_off(p * 8 + r0, q);
-            uint4 hi;
-            hi.x = tf32_rna(v[p].x); hi.y = tf32_rna(v[p].y); hi.z = tf32_rna(v[p].z); hi.w = tf32_rna(v[p].w);
-            sts128(stA + off, hi);
-            if (C::NS == 2) {
-              uint4 lo;
-              lo.x = tf32_rna(v[p].x - __uint_as_float(hi.x)); lo.y = tf32_rna(v[p].y - __uint_as_float(hi.y));
-              lo.z = tf32_rna(v[p].z - __uint_as_float(hi.z)); lo.w = tf32_rna(v[p].w - __uint_as_float(hi.w));
-              sts128(stA + C::A_PART + off, lo);
+            for (int p = 0; p < 16; ++p) v[p] = __ldg(reinterpret_cast<const float4 *>(src + rowoff[hb * 16 + p] + q * 4));
+#pragma unroll
+            for (int p = 0; p < 16; ++p) {
+              const int r = (hb * 16 + p) * 8 + r0;          // row within the 256-row tile
+              const uint32_t dst = stA + (r >> 7) * C::A_SUB + sw64_off(r & 127, q);
+              uint4 hi;
+              hi.x = tf32_rna(v[p].x); hi.y = tf32_rna(v[p].y); hi.z = tf32_rna(v[p].z); hi.w = tf32_rna(v[p].w);
+              sts128(dst, hi);
+              if (C::NS == 2) {
+                uint4 lo;
+                lo.x = tf32_rna(v[p].x - __uint_as_float(hi.x)); lo.y = tf32_rna(v[p].y - __uint_as_float(hi.y));
+                lo.z = tf32_rna(v[p].z - __uint_as_float(hi.z)); lo.w = tf32_rna(v[p].w - __uint_as_float(hi.w));
+                sts128(dst + C::A_PART, lo);
+              }
             }
           }
         } else {
 #pragma unroll
-          for (int half = 0; half < 2; ++half) {
+          for (int hb = 0; hb < 4; ++hb) {                 // four batches of 8 rows (2 float4 each) per lane
             float4 v[16];
 #pragma unroll
             for (int p = 0; p < 8; ++p) {
-              const float *s = src + rowoff[half * 8 + p] + q * 8;
-              v[2 * p] = __ldg(reinterpret_cast<const float4 *>(s));
-              v[2 * p + 1] = __ldg(reinterpret_cast<const float4 *>(s + 4));
+              const float *sp = src + rowoff[hb * 8 + p] + q * 8;
+              v[2 * p] = __ldg(reinterpret_cast<const float4 *>(sp));
+              v[2 * p + 1] = __ldg(reinterpret_cast<const float4 *>(sp + 4));
             }
 #pragma unroll
             for (int p = 0; p < 8; ++p) {
-              const uint32_t off = sw64_off((half * 8 + p) * 8 + r0, q);
+              const int r = (hb * 8 + p) * 8 + r0;
+              const uint32_t dst = stA + (r >> 7) * C::A_SUB + sw64_off(r & 127, q);
               const float f[8] = {v[2 * p].x, v[2 * p].y, v[2 * p].z, v[2 * p].w, v[2 * p + 1].x, v[2 * p + 1].y, v[2 * p + 1].z, v[2 * p + 1].w};
               float h[8];
 #pragma unroll
               for (int i = 0; i < 8; ++i) h[i] = __bfloat162float(__float2bfloat16_rn(f[i]));
               uint4 hi;
               hi.x = pack_bf16(h[0], h[1]); hi.y = pack_bf16(h[2], h[3]); hi.z = pack_bf16(h[4], h[5]); hi.w = pack_bf16(h[6], h[7]);
-              sts128(stA + off, hi);
+              sts128(dst, hi);
               if (C::NS == 2) {
                 uint4 lo;
                 lo.x = pack_bf16(f[0] - h[0], f[1] - h[1]); lo.y = pack_bf16(f[2] - h[2], f[3] - h[3]);
                 lo.z = pack_bf16(f[4] - h[4], f[5] - h[5]); lo.w = pack_bf16(f[6] - h[6], f[7] - h[7]);
-                sts128(stA + C::A_PART + off, lo);
+                sts128(dst + C::A_PART, lo);
               }
             }
           }
         }
         fence_proxy_async();
-        mbar_arrive(&full_bar[w]);
-        ++uses;
+        mbar_arrive(&full_bar[s]);
       }
     }
-  } else if (warp == 8) {
+  } else if (warp == WARP_BLOAD) {
     // ================================ B loader ==================================================
     if (lane == 0) {
       uint32_t g = 0;
@@ -301,71 +333,81 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const GemmArgs A) {
         const int grp = A.tile_type ? __ldg(&A.tile_type[mt]) : 0;
         const uint8_t *blob = A.b_blob + ((size_t)(grp * A.n_tiles + nt) * NKC) * C::B_STAGE;
         for (int kc = 0; kc < NKC; ++kc, ++g) {
-          const int s = g % NSTAGE;
-          mbar_wait(&empty_bar[s], ((g / NSTAGE) & 1) ^ 1);
+          const uint32_t s = g % C::NSTAGE;
+          mbar_wait(&empty_bar[s], ((g / C::NSTAGE) & 1) ^ 1);
+          if (A.dbg & 2) {
+            mbar_arrive(&full_bar[s]);
+            continue;
+          }
           mbar_arrive_expect_tx(&full_bar[s], C::B_STAGE);
           bulk_g2s(smem + s * C::STAGE + C::A_STAGE, blob + (size_t)kc * C::B_STAGE, C::B_STAGE, &full_bar[s]);
         }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == WARP_MMA) {
     // ================================ MMA issuer ================================================
     if (lane == 0) {
       uint32_t g = 0, tcount = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
-        const uint32_t buf = tcount & 1;
-        mbar_wait(&tempty_bar[buf], ((tcount >> 1) & 1) ^ 1);
+        const uint32_t buf = tcount % C::NBUF;
+        mbar_wait(&tempty_bar[buf], ((tcount / C::NBUF) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + buf * C::NTILE;
+        const uint32_t d_tmem = tmem_base + buf * C::ACC_COLS;
         for (int kc = 0; kc < NKC; ++kc, ++g) {
-          const int s = g % NSTAGE;
-          mbar_wait(&full_bar[s], (g / NSTAGE) & 1);
+          const uint32_t s = g % C::NSTAGE;
+          mbar_wait(&full_bar[s], (g / C::NSTAGE) & 1);
           tc_fence_after();
-          const uint32_t a_hi = smem_u32(smem + s * C::STAGE), a_lo = a_hi + C::A_PART;
-          const uint32_t b_hi = a_hi + C::A_STAGE, b_lo = b_hi + C::B_PART;
+          const uint32_t a0 = smem_u32(smem + s * C::STAGE);
+          const uint32_t b_hi = a0 + C::A_STAGE, b_lo = b_hi + C::B_PART;
 #pragma unroll
-          for (int ks = 0; ks < C::KSTEPS; ++ks) {
+          for (int ks = 0; ks < ((A.dbg & 8) ? 0 : C::KSTEPS); ++ks) {
             const uint32_t ko = ks * 32;
-            if (C::NSPLIT == 3) {
-              umma<C::KIND>(d_tmem, smem_desc_sw64(a_lo + ko), smem_desc_sw64(b_hi + ko), C::IDESC, (kc | ks) != 0);
-              umma<C::KIND>(d_tmem, smem_desc_sw64(a_hi + ko), smem_desc_sw64(b_lo + ko), C::IDESC, 1);
-              umma<C::KIND>(d_tmem, smem_desc_sw64(a_hi + ko), smem_desc_sw64(b_hi + ko), C::IDESC, 1);
-            } else {
-              umma<C::KIND>(d_tmem, smem_desc_sw64(a_hi + ko), smem_desc_sw64(b_hi + ko), C::IDESC, (kc | ks) != 0);
+#pragma unroll
+            for (int sub = 0; sub < C::SUB; ++sub) {
+              const uint32_t a_hi = a0 + sub * C::A_SUB, a_lo = a_hi + C::A_PART;
+              const uint32_t d = d_tmem + sub * C::NTILE;
+              if (C::NSPLIT == 3) {
+                umma<C::KIND>(d, smem_desc_sw64(a_lo + ko), smem_desc_sw64(b_hi + ko), C::IDESC, (kc | ks) != 0);
+                umma<C::KIND>(d, smem_desc_sw64(a_hi + ko), smem_desc_sw64(b_lo + ko), C::IDESC, 1);
+                umma<C::KIND>(d, smem_desc_sw64(a_hi + ko), smem_desc_sw64(b_hi + ko), C::IDESC, 1);
+              } else {
+                umma<C::KIND>(d, smem_desc_sw64(a_hi + ko), smem_desc_sw64(b_hi + ko), C::IDESC, (kc | ks) != 0);
+              }
             }
           }
           umma_commit(&empty_bar[s]);        // frees the smem stage once these MMAs have read it
         }
-        umma_commit(&tfull_bar[buf]);        // accumulator complete -> epilogue
+        umma_commit(&tfull_bar[buf]);        // accumulators complete -> epilogue
       }
     }
-  } else {
-    // ================================ epilogue (warps 0-3 <-> TMEM lanes 32w..32w+31) ============
+  } else if (warp < NUM_EPI_WARPS) {
+    // ============== epilogue: warp w <-> sub-tile (w >> 2), TMEM lanes 32 (w & 3) .. +31 ==========
     uint32_t tcount = 0;
-    const int rloc = warp * 32 + lane;
+    const int quarter = warp & 3, sub = warp >> 2;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
-      const uint32_t buf = tcount & 1;
+      const uint32_t buf = tcount % C::NBUF;
       const int mt = tile / A.n_tiles, nt = tile % A.n_tiles;
-      const size_t row = (size_t)mt * TILE_M + rloc;
-      const uint32_t taddr = tmem_base + buf * C::NTILE + ((uint32_t)(warp * 32) << 16);
+      const size_t row = (size_t)mt * C::TILE_ROWS + sub * SUB_M + quarter * 32 + lane;
+      const uint32_t taddr = tmem_base + buf * C::ACC_COLS + sub * C::NTILE + ((uint32_t)(quarter * 32) << 16);
       if (C::EPI == EPI_TC_L1) {
         const int grp = A.tile_type ? __ldg(&A.tile_type[mt]) : 0;
         const float4 *Sv = reinterpret_cast<const float4 *>(A.S + row * CCSP_H2 + nt * C::NTILE);
         float4 *Hv = reinterpret_cast<float4 *>(A.H + row * CCSP_H2 + nt * C::NTILE);
         float4 sn[8];                                       // static term, prefetched one 32-column chunk ahead
 #pragma unroll
-        for (int qq = 0; qq < 8; ++qq) sn[qq] = ldg_nc_f4(Sv + qq);
-        asm volatile("bar.sync 1, 128;" ::: "memory");      // previous tile's readers of epi_const are done
-        for (int i = threadIdx.x; i < C::NTILE; i += 128) epi_const[i] = __ldg(&A.tb[(size_t)grp * CCSP_H2 + nt * C::NTILE + i]);
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        mbar_wait(&tfull_bar[buf], (tcount >> 1) & 1);
+        for (int qq = 0; qq < 8; ++qq) sn[qq] = (A.dbg & 4) ? make_float4(0.f, 0.f, 0.f, 0.f) : ldg_nc_f4(Sv + qq);
+        asm volatile("bar.sync 1, 256;" ::: "memory");      // previous tile's readers of epi_const are done
+        for (int i = threadIdx.x; i < C::NTILE; i += NUM_EPI_WARPS * 32)
+          epi_const[i] = __ldg(&A.tb[(size_t)grp * CCSP_H2 + nt * C::NTILE + i]);
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        mbar_wait(&tfull_bar[buf], (tcount / C::NBUF) & 1);
         tc_fence_after();
 #pragma unroll 1
         for (int cb = 0; cb < C::NTILE; cb += 32) {
           float4 sc[8];
 #pragma unroll
           for (int qq = 0; qq < 8; ++qq) sc[qq] = sn[qq];
-          if (cb + 32 < C::NTILE) {
+          if (cb + 32 < C::NTILE && !(A.dbg & 4)) {
 #pragma unroll
             for (int qq = 0; qq < 8; ++qq) sn[qq] = ldg_nc_f4(Sv + (cb + 32) / 4 + qq);
           }
@@ -377,11 +419,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const GemmArgs A) {
             float4 o4;
             o4.x = silu_fast(v[4 * qq] + sc[qq].x + t4.x); o4.y = silu_fast(v[4 * qq + 1] + sc[qq].y + t4.y);
             o4.z = silu_fast(v[4 * qq + 2] + sc[qq].z + t4.z); o4.w = silu_fast(v[4 * qq + 3] + sc[qq].w + t4.w);
-            Hv[cb / 4 + qq] = o4;
+            if (!(A.dbg & 4) || o4.x == 12345.678f) Hv[cb / 4 + qq] = o4;
           }
         }
       } else {
-        mbar_wait(&tfull_bar[buf], (tcount >> 1) & 1);
+        mbar_wait(&tfull_bar[buf], (tcount / C::NBUF) & 1);
         tc_fence_after();
         const float *bd1 = epi_const, *w2t = epi_const + CCSP_HH, *bd2 = epi_const + CCSP_HH + CCSP_MAXP * CCSP_HH;
         if (A.P <= 4) {
@@ -433,7 +475,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const GemmArgs A) {
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) tmem_dealloc(tmem_base, C::TMEM_COLS);
+  if (warp == WARP_MMA) tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
 
 // ---------------------------------------------------------------------------------------------------

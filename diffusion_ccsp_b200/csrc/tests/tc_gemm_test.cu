@@ -52,7 +52,7 @@ static Problem make_problem(int n_nodes, int m_tiles, int groups, unsigned seed)
   p.n_nodes = n_nodes; p.m_tiles = m_tiles; p.groups = groups; p.P = 4;
   std::mt19937 rng(seed);
   std::uniform_real_distribution<float> u(-1.f, 1.f);
-  const int rows = m_tiles * 128;
+  const int rows = m_tiles * 256;
   p.node_emb.resize((size_t)(n_nodes + 1) * 256);
   for (auto &v : p.node_emb) v = u(rng);
   for (int k = 0; k < 256; ++k) p.node_emb[(size_t)n_nodes * 256 + k] = 0.f;
@@ -84,8 +84,8 @@ static std::vector<uint8_t> pack_l1(const Problem &p) {
 struct Report { double max_err, max_ref, ms; };
 
 template <class C>
-static Report run_l1(const Problem &p, const std::vector<double> *ref, int iters, int num_sms) {
-  const int rows = p.m_tiles * 128;
+static Report run_l1(const Problem &p, const std::vector<double> *ref, int iters, int num_sms, int dbg = 0) {
+  const int rows = p.m_tiles * 256;
   float *d_emb = dev(p.node_emb), *d_S = dev(p.S), *d_tb = dev(p.tb), *d_H;
   int *d_i0 = dev(p.idx0), *d_i1 = dev(p.idx1), *d_tt = dev(p.tile_type);
   std::vector<uint8_t> blob = pack_l1<C>(p);
@@ -96,7 +96,7 @@ static Report run_l1(const Problem &p, const std::vector<double> *ref, int iters
   memset(&a, 0, sizeof(a));
   a.a_src[0] = d_emb; a.a_src[1] = d_emb; a.a_idx[0] = d_i0; a.a_idx[1] = d_i1; a.nseg = 2;
   a.b_blob = d_blob; a.tile_type = d_tt; a.num_m_tiles = p.m_tiles; a.n_tiles = 512 / C::NTILE;
-  a.S = d_S; a.tb = d_tb; a.H = d_H;
+  a.S = d_S; a.tb = d_tb; a.H = d_H; a.dbg = dbg;
   CK(launch_gemm_tc<C>(a, num_sms, 0));
   CK(cudaDeviceSynchronize());
   Report rep{0, 0, 0};
@@ -138,7 +138,7 @@ static Report run_dec(const Problem &p, const std::vector<float> &Hin, const std
   CK(cudaMemset(d_o, 0xFF, (size_t)rows * p.P * sizeof(float)));
   GemmArgs a;
   memset(&a, 0, sizeof(a));
-  a.a_src[0] = d_H; a.nseg = 1; a.b_blob = d_blob; a.num_m_tiles = rows / 128; a.n_tiles = 1;
+  a.a_src[0] = d_H; a.nseg = 1; a.b_blob = d_blob; a.num_m_tiles = rows / 256; a.n_tiles = 1;
   a.bd1 = d_bd1; a.Wd2 = d_w2; a.bd2 = d_bd2; a.P = p.P; a.o = d_o;
   CK(launch_gemm_tc<C>(a, num_sms, 0));
   CK(cudaDeviceSynchronize());
@@ -176,14 +176,14 @@ int main(int argc, char **argv) {
   printf("device %s, %d SMs, smem/block optin %zu\n", prop.name, sms, prop.sharedMemPerBlockOptin);
   int fails = 0;
   {
-    // ---- numerics: 21 tiles (ragged vs the 148-SM grid on purpose), 3 weight groups ------------------
-    Problem p = make_problem(1000, 21, 3, 1);
-    const int rows = p.m_tiles * 128;
+    // ---- numerics: 11 tiles of 256 rows, 3 weight groups ---------------------------------------------
+    Problem p = make_problem(1000, 11, 3, 1);
+    const int rows = p.m_tiles * 256;
     std::vector<double> ref((size_t)rows * 512);
     std::vector<float> Href((size_t)rows * 512);
     for (int r = 0; r < rows; ++r) {
       const float *a0 = &p.node_emb[(size_t)p.idx0[r] * 256], *a1 = &p.node_emb[(size_t)p.idx1[r] * 256];
-      const int g = p.tile_type[r / 128];
+      const int g = p.tile_type[r / 256];
       for (int n = 0; n < 512; ++n) {
         const float *w = &p.W[((size_t)g * 512 + n) * 512];
         double acc = 0;
@@ -222,16 +222,28 @@ int main(int argc, char **argv) {
     chk("dec bf16", run_dec<Cfg<KIND_BF16, 1, 128, EPI_TC_DEC>>(p, Href, &oref, 0, sms), 4e-2);
   }
   if (perf && fails == 0) {
-    // ---- throughput at the config-2 size: 633 edge tiles (81 024 rows), 13 weight groups ---------------
-    Problem p = make_problem(9216, 633, 13, 2);
-    const double fl1 = 2.0 * 633 * 128 * 512 * 512, fdec = 2.0 * 633 * 256 * 128 * 256;
-    std::vector<float> Hin((size_t)633 * 128 * 512);
+    // ---- throughput at the config-2 size: 317 edge tiles (81 152 rows), 13 weight groups ---------------
+    Problem p = make_problem(9216, 317, 13, 2);
+    const double fl1 = 2.0 * 317 * 256 * 512 * 512, fdec = 2.0 * 317 * 512 * 128 * 256;
+    std::vector<float> Hin((size_t)317 * 256 * 512);
     for (size_t i = 0; i < Hin.size(); ++i) Hin[i] = (float)((i * 2654435761u) % 1000) / 1000.f - 0.5f;
-    auto pr = [&](const char *name, Report r, double fl) { printf("%-22s %.3f ms  %.1f TFLOP/s (algorithmic)\n", name, r.ms, fl / r.ms / 1e9); };
+    auto pr = [&](const char *name, Report r, double fl) { printf("%-34s %.3f ms  %.1f TFLOP/s (algorithmic)\n", name, r.ms, fl / r.ms / 1e9); };
     pr("l1  tf32x3", run_l1<Cfg<KIND_TF32, 3, 256, EPI_TC_L1>>(p, nullptr, 20, sms), fl1);
     pr("l1  bf16x3", run_l1<Cfg<KIND_BF16, 3, 256, EPI_TC_L1>>(p, nullptr, 20, sms), fl1);
     pr("l1  tf32", run_l1<Cfg<KIND_TF32, 1, 256, EPI_TC_L1>>(p, nullptr, 20, sms), fl1);
     pr("l1  bf16", run_l1<Cfg<KIND_BF16, 1, 256, EPI_TC_L1>>(p, nullptr, 20, sms), fl1);
+    const char *abl[] = {"none", "noA", "noB", "noA,noB", "noEpiIO", "noA,noEpiIO", "noB,noEpiIO", "MMA+sync only",
+                         "noMMA", "noMMA,noA", "noMMA,noB", "noMMA,noA,noB", "noMMA,noEpiIO", "", "", "sync skeleton"};
+    for (int dbg : {1, 2, 3, 4, 7, 8, 9, 10, 12, 15}) {
+      char nm[64];
+      snprintf(nm, sizeof nm, "l1 tf32x3 [%s]", abl[dbg]);
+      pr(nm, run_l1<Cfg<KIND_TF32, 3, 256, EPI_TC_L1>>(p, nullptr, 10, sms, dbg), fl1);
+    }
+    for (int dbg : {1, 2, 4, 7, 8}) {
+      char nm[64];
+      snprintf(nm, sizeof nm, "l1 bf16x3 [%s]", abl[dbg]);
+      pr(nm, run_l1<Cfg<KIND_BF16, 3, 256, EPI_TC_L1>>(p, nullptr, 10, sms, dbg), fl1);
+    }
     pr("dec tf32x3", run_dec<Cfg<KIND_TF32, 3, 128, EPI_TC_DEC>>(p, Hin, nullptr, 20, sms), fdec);
     pr("dec bf16x3", run_dec<Cfg<KIND_BF16, 3, 128, EPI_TC_DEC>>(p, Hin, nullptr, 20, sms), fdec);
     pr("dec tf32", run_dec<Cfg<KIND_TF32, 1, 128, EPI_TC_DEC>>(p, Hin, nullptr, 20, sms), fdec);
