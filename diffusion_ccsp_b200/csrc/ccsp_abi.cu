@@ -113,11 +113,14 @@ struct CcspPlan {
   int *src_i = nullptr, *src_j = nullptr, *tile_type = nullptr, *node_ptr = nullptr, *node_src = nullptr;
   signed char *mask = nullptr;
   float *gt = nullptr, *xtail = nullptr;
-  float *S = nullptr;             // [Epad, 512] static pre-activation
-  float *H = nullptr;             // [Epad, 512] first-layer activations
+  float *S = nullptr;             // [Epad, 512] static pre-activation, blocked layout (common.cuh blk_off)
   float *o = nullptr;             // [Epad, 2, P] decoder outputs
-  float *pe = nullptr;            // [n+1, 256] pose embeddings (row n = zeros for padded edges)
   float *x = nullptr;             // [n, P] sampler state
+  // per-arithmetic-mode work buffers, allocated on first use (ensure_mode_buffers)
+  float *pe32 = nullptr;          // FP32 path: [n+1, 256] pose embeddings (row n = zeros for padded edges)
+  float *H32 = nullptr;           // FP32 path: [Epad, 512] first-layer activations, row-major
+  uint8_t *pe_split[2] = {nullptr, nullptr};   // tensor-core paths, per operand kind (TF32 / BF16): [n+1][256 hi | 256 lo]
+  uint8_t *Hop[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // per math mode: H in decoder-operand format
   int64_t h2d_bytes = 0;
   // sampled kernel timing (bench roofline)
   int timing_stride = 0;
@@ -226,19 +229,16 @@ static int ensure_time_table(CcspModel *m, int T, cudaStream_t st) {
 }
 
 // ---- tensor-core modes -----------------------------------------------------------------------------
-template <int KIND, int NSPLIT> using L1Cfg = tc::Cfg<KIND, NSPLIT, 256, tc::EPI_TC_L1>;
-template <int KIND, int NSPLIT> using DecCfg = tc::Cfg<KIND, NSPLIT, 128, tc::EPI_TC_DEC>;
-
-template <int KIND, int NSPLIT>
+template <class M>
 static int pack_tc_blobs(CcspModel *m, int math) {
-  using L1 = L1Cfg<KIND, NSPLIT>;
-  using Dec = DecCfg<KIND, NSPLIT>;
-  const size_t per = (size_t)2 * (CCSP_H2 / L1::KC) * L1::B_STAGE;
+  using L1 = tc::L1Cfg<M>;
+  using Dec = tc::DecCfg<M>;
+  const size_t per = (size_t)2 * M::NKC1 * L1::B_STAGE;
   std::vector<uint8_t> b1(per * m->C);
   for (int c = 0; c < m->C; ++c)
-    tc::pack_b_blob<L1>(&m->h_pose_w[(size_t)c * CCSP_H2 * CCSP_H2], CCSP_H2, 0, CCSP_H2, CCSP_H2, b1.data() + c * per);
-  std::vector<uint8_t> b2((size_t)(CCSP_H / Dec::KC) * Dec::B_STAGE);
-  tc::pack_b_blob<Dec>(m->h_dec_w1.data(), CCSP_H, 0, CCSP_H, CCSP_HH, b2.data());
+    tc::pack_b_blob<M, 256>(&m->h_pose_w[(size_t)c * CCSP_H2 * CCSP_H2], CCSP_H2, 0, CCSP_H2, CCSP_H2, b1.data() + c * per);
+  std::vector<uint8_t> b2((size_t)M::NKC2 * Dec::B_STAGE);
+  tc::pack_b_blob<M, 128>(m->h_dec_w1.data(), CCSP_H, 0, CCSP_H, CCSP_HH, b2.data());
   CCSP_CUDA_TRY(upload(m->pool, &m->blob_l1[math], b1));
   CCSP_CUDA_TRY(upload(m->pool, &m->blob_dec[math], b2));
   return CCSP_OK;
@@ -247,34 +247,54 @@ static int pack_tc_blobs(CcspModel *m, int math) {
 static int ensure_tc_blobs(CcspModel *m, int math) {
   if (math == CCSP_MATH_FP32 || m->blob_l1[math]) return CCSP_OK;
   switch (math) {
-    case CCSP_MATH_TF32X3: return pack_tc_blobs<tc::KIND_TF32, 3>(m, math);
-    case CCSP_MATH_BF16X3: return pack_tc_blobs<tc::KIND_BF16, 3>(m, math);
-    case CCSP_MATH_TF32: return pack_tc_blobs<tc::KIND_TF32, 1>(m, math);
-    case CCSP_MATH_BF16: return pack_tc_blobs<tc::KIND_BF16, 1>(m, math);
+    case CCSP_MATH_TF32X3: return pack_tc_blobs<tc::Mode<tc::KIND_TF32, 3>>(m, math);
+    case CCSP_MATH_BF16X3: return pack_tc_blobs<tc::Mode<tc::KIND_BF16, 3>>(m, math);
+    case CCSP_MATH_TF32: return pack_tc_blobs<tc::Mode<tc::KIND_TF32, 1>>(m, math);
+    case CCSP_MATH_BF16: return pack_tc_blobs<tc::Mode<tc::KIND_BF16, 1>>(m, math);
   }
   set_error("unknown math mode");
   return CCSP_ERR_INVALID;
 }
 
-template <int KIND, int NSPLIT>
+static inline int math_kind(int math) { return (math == CCSP_MATH_TF32X3 || math == CCSP_MATH_TF32) ? 0 : 1; }
+static inline int math_ns(int math) { return (math == CCSP_MATH_TF32X3 || math == CCSP_MATH_BF16X3) ? 2 : 1; }
+
+// work buffers of the plan for the model's current arithmetic mode
+static int ensure_mode_buffers(CcspPlan *p) {
+  CcspModel *m = p->m;
+  if (m->math == CCSP_MATH_FP32) {
+    if (!p->pe32) {
+      CCSP_CUDA_TRY(p->pool.alloc(&p->pe32, (size_t)(p->n + 1) * CCSP_H));
+      CCSP_CUDA_TRY(p->pool.alloc(&p->H32, (size_t)p->Epad * CCSP_H2));
+    }
+    return CCSP_OK;
+  }
+  const int kind = math_kind(m->math), elt = kind == 0 ? 4 : 2;
+  if (!p->pe_split[kind]) CCSP_CUDA_TRY(p->pool.alloc(&p->pe_split[kind], (size_t)(p->n + 1) * 2 * CCSP_H * elt));
+  if (!p->Hop[m->math]) CCSP_CUDA_TRY(p->pool.alloc(&p->Hop[m->math], (size_t)p->Epad * CCSP_H2 * elt * math_ns(m->math)));
+  return CCSP_OK;
+}
+
+template <class M>
 static int launch_edge_tc(CcspPlan *p, const float *tb, cudaStream_t st, cudaEvent_t mid) {
   CcspModel *m = p->m;
-  tc::GemmArgs a;
+  tc::L1Args a;
   std::memset(&a, 0, sizeof(a));
-  a.a_src[0] = p->pe; a.a_src[1] = p->pe; a.a_idx[0] = p->src_i; a.a_idx[1] = p->src_j; a.nseg = 2;
+  a.pe_split = p->pe_split[math_kind(m->math)];
+  a.src_i = p->src_i; a.src_j = p->src_j;
   a.b_blob = m->blob_l1[m->math]; a.tile_type = p->tile_type;
-  a.num_m_tiles = (int)(p->Epad / CCSP_TILE_M); a.n_tiles = 2;
-  a.S = p->S; a.tb = tb; a.H = p->H;
-  CCSP_CUDA_TRY((tc::launch_gemm_tc<L1Cfg<KIND, NSPLIT>>(a, m->num_sms, st)));
+  a.num_m_tiles = (int)(p->Epad / CCSP_TILE_M);
+  a.S = p->S; a.tb = tb; a.H = p->Hop[m->math];
+  CCSP_CUDA_TRY((tc::launch_l1_tc<M>(a, m->num_sms, st)));
   count_launch();
   if (mid) CCSP_CUDA_TRY(cudaEventRecord(mid, st));
-  tc::GemmArgs d;
+  tc::DecArgs d;
   std::memset(&d, 0, sizeof(d));
-  d.a_src[0] = p->H; d.nseg = 1;
+  d.H = p->Hop[m->math];
   d.b_blob = m->blob_dec[m->math];
-  d.num_m_tiles = (int)(2 * p->Epad / CCSP_TILE_M); d.n_tiles = 1;
+  d.num_tiles = (int)(2 * p->Epad / CCSP_TILE_M);
   d.bd1 = m->dec_b1; d.Wd2 = m->dec_w2; d.bd2 = m->dec_b2; d.P = m->P; d.o = p->o;
-  CCSP_CUDA_TRY((tc::launch_gemm_tc<DecCfg<KIND, NSPLIT>>(d, m->num_sms, st)));
+  CCSP_CUDA_TRY((tc::launch_dec_tc<M>(d, m->num_sms, st)));
   count_launch();
   return CCSP_OK;
 }
@@ -283,27 +303,27 @@ static int launch_edge_tc(CcspPlan *p, const float *tb, cudaStream_t st, cudaEve
 static int launch_edge(CcspPlan *p, int t, cudaStream_t st, cudaEvent_t mid = nullptr) {
   CcspModel *m = p->m;
   if (p->Epad == 0) return CCSP_OK;
-  RowSrc rs;
-  rs.nseg = 2;
-  rs.src[0] = p->pe; rs.idx[0] = p->src_i;
-  rs.src[1] = p->pe; rs.idx[1] = p->src_j;
-  rs.src[2] = nullptr; rs.idx[2] = nullptr;
   const float *tb = m->tb + (size_t)t * m->C * CCSP_H2;
   switch (m->math) {
     case CCSP_MATH_FP32: {
+      RowSrc rs;
+      rs.nseg = 2;
+      rs.src[0] = p->pe32; rs.idx[0] = p->src_i;
+      rs.src[1] = p->pe32; rs.idx[1] = p->src_j;
+      rs.src[2] = nullptr; rs.idx[2] = nullptr;
       k_edge_l1_simt<EPI_L1><<<dim3((unsigned)(p->Epad / SG_BM), CCSP_H2 / SG_BN), 256, 0, st>>>(
-          rs, m->Wpt, p->tile_type, m->bias, p->S, tb, p->H);
+          rs, m->Wpt, p->tile_type, m->bias, p->S, tb, p->H32);
       CCSP_LAUNCH_CHECK();
       if (mid) CCSP_CUDA_TRY(cudaEventRecord(mid, st));
-      k_edge_dec_simt<<<(unsigned)(2 * p->Epad / SG_BM), 256, 0, st>>>(p->H, m->dec_w1t, m->dec_b1, m->dec_w2,
+      k_edge_dec_simt<<<(unsigned)(2 * p->Epad / SG_BM), 256, 0, st>>>(p->H32, m->dec_w1t, m->dec_b1, m->dec_w2,
                                                                        m->dec_b2, m->P, p->o);
       CCSP_LAUNCH_CHECK();
       return CCSP_OK;
     }
-    case CCSP_MATH_TF32X3: return launch_edge_tc<tc::KIND_TF32, 3>(p, tb, st, mid);
-    case CCSP_MATH_BF16X3: return launch_edge_tc<tc::KIND_BF16, 3>(p, tb, st, mid);
-    case CCSP_MATH_TF32: return launch_edge_tc<tc::KIND_TF32, 1>(p, tb, st, mid);
-    case CCSP_MATH_BF16: return launch_edge_tc<tc::KIND_BF16, 1>(p, tb, st, mid);
+    case CCSP_MATH_TF32X3: return launch_edge_tc<tc::Mode<tc::KIND_TF32, 3>>(p, tb, st, mid);
+    case CCSP_MATH_BF16X3: return launch_edge_tc<tc::Mode<tc::KIND_BF16, 3>>(p, tb, st, mid);
+    case CCSP_MATH_TF32: return launch_edge_tc<tc::Mode<tc::KIND_TF32, 1>>(p, tb, st, mid);
+    case CCSP_MATH_BF16: return launch_edge_tc<tc::Mode<tc::KIND_BF16, 1>>(p, tb, st, mid);
     default:
       set_error("unknown math mode");
       return CCSP_ERR_STATE;
@@ -318,7 +338,11 @@ static NodeArgs node_args_base(CcspPlan *p) {
   a.x = p->x; a.o = p->o; a.node_ptr = p->node_ptr; a.node_src = p->node_src;
   a.mask = p->mask; a.gt = p->gt; a.xtail = p->xtail;
   a.W0 = m->pose.w0; a.b0 = m->pose.b0; a.W2t = m->pose.w2t; a.b2 = m->pose.b2;
-  a.pe = p->pe;
+  if (m->math == CCSP_MATH_FP32) {
+    a.pe_fmt = 0; a.pe = p->pe32;
+  } else {
+    a.pe_fmt = 1 + math_kind(m->math); a.pe = p->pe_split[math_kind(m->math)];
+  }
   return a;
 }
 
@@ -469,9 +493,7 @@ int ccsp_plan_create(CcspModel *m, const float *x, int64_t n, int32_t F, const i
   PLAN_TRY(upload(p->pool, &p->gt, gt));
   PLAN_TRY(upload(p->pool, &p->xtail, xtail));
   PLAN_TRY(p->pool.alloc(&p->S, (size_t)Epad * CCSP_H2));
-  PLAN_TRY(p->pool.alloc(&p->H, (size_t)Epad * CCSP_H2));
   PLAN_TRY(p->pool.alloc(&p->o, (size_t)Epad * 2 * P));
-  PLAN_TRY(p->pool.alloc(&p->pe, (size_t)(n + 1) * CCSP_H));
   PLAN_TRY(p->pool.alloc(&p->x, (size_t)n * P));
   PLAN_TRY(cudaMemsetAsync(p->o, 0, (size_t)Epad * 2 * P * sizeof(float), st));
 
@@ -569,6 +591,7 @@ int ccsp_denoise(CcspPlan *p, const float *poses, int32_t t, float *out, void *s
   cudaStream_t st = (cudaStream_t)stream;
   int rc;
   if ((rc = ensure_time_table(p->m, t + 1, st))) return rc;
+  if ((rc = ensure_mode_buffers(p))) return rc;
   NodeArgs a = node_args_base(p);
   a.mode = NODE_ENCODE; a.x_in = poses;
   if ((rc = launch_node(p, a, st))) return rc;
@@ -592,6 +615,7 @@ int ccsp_sample(CcspPlan *p, const CcspSchedule *s, const CcspNoise *nz, float *
   const size_t nP = (size_t)p->n * m->P;
   int rc;
   if ((rc = ensure_time_table(m, T, st))) return rc;
+  if ((rc = ensure_mode_buffers(p))) return rc;
 
   // sampled kernel timing: evaluation `ev_idx` is bracketed by events when selected
   long ev_idx = 0;

@@ -7,7 +7,7 @@
 #define CCSP_H 256            // hidden_dim
 #define CCSP_H2 512           // 2 * hidden_dim (first-layer output width, one half per edge endpoint)
 #define CCSP_HH 128           // hidden_dim / 2
-#define CCSP_TILE_M 256       // edge rows per tile (padded per constraint type)
+#define CCSP_TILE_M 128       // edge rows per tile (padded per constraint type)
 #define CCSP_MAXP 8
 
 namespace ccsp {
@@ -36,6 +36,14 @@ void count_launch();
       return CCSP_ERR_CUDA;                                                                          \
     }                                                                                                \
   } while (0)
+
+// ---- blocked layout of the per-edge static term S [Epad, 512] ------------------------------------
+// 32-row x 32-column blocks; inside a block: 8 pieces (4 floats each) x 32 rows x 16 B, so that a warp
+// whose lanes own 32 consecutive rows reads/writes 512 contiguous bytes per instruction (the access
+// pattern of a TMEM-lane-per-thread epilogue).  Returns the float offset of element (row, col).
+__host__ __device__ __forceinline__ size_t blk_off(size_t row, int col) {
+  return ((((row >> 5) * 16 + (size_t)(col >> 5)) * 8 + (size_t)((col & 31) >> 2)) * 32 + (row & 31)) * 4 + (col & 3);
+}
 
 // ---- activations (torch.nn.SiLU / torch.nn.Mish semantics, accurate libm versions) -------------
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + expf(-x)); }

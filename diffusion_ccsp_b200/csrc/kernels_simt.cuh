@@ -7,6 +7,8 @@
 //
 // Reference semantics cited per kernel (paths relative to the reference checkout).
 #pragma once
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace ccsp {
@@ -149,7 +151,8 @@ struct NodeArgs {
   const signed char *mask;       // [n]
   const float *gt, *xtail;       // [n,P]
   const float *W0, *b0, *W2t, *b2;   // pose encoder
-  float *pe;                     // [n+1, 256]
+  int pe_fmt;                    // 0: FP32 [n+1,256]; 1: TF32 split, 2: BF16 split  ([n+1][256 hi | 256 lo], kernels_tc.cuh)
+  void *pe;
 };
 
 __global__ void __launch_bounds__(256) k_node(NodeArgs A) {
@@ -217,8 +220,25 @@ __global__ void __launch_bounds__(256) k_node(NodeArgs A) {
   encoder_rows_16(xs, P, A.W0, A.b0, A.W2t, A.b2, h, o);
 #pragma unroll
   for (int r = 0; r < ENC_ROWS; ++r) {
-    int v = row0 + r;
-    if (v <= A.n) A.pe[(size_t)v * CCSP_H + tid] = v < A.n ? o[r] : 0.f;
+    const int v = row0 + r;
+    if (v > A.n) continue;
+    const float e = v < A.n ? o[r] : 0.f;
+    if (A.pe_fmt == 0) {
+      reinterpret_cast<float *>(A.pe)[(size_t)v * CCSP_H + tid] = e;
+    } else if (A.pe_fmt == 1) {          // hi = rna_tf32(e), lo = rna_tf32(e - hi)
+      uint32_t hi, lo;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(e));
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(e - __uint_as_float(hi)));
+      uint32_t *row = reinterpret_cast<uint32_t *>(A.pe) + (size_t)v * (2 * CCSP_H);
+      row[tid] = hi;
+      row[CCSP_H + tid] = lo;
+    } else {                             // hi = rn_bf16(e), lo = rn_bf16(e - hi)
+      const __nv_bfloat16 hi = __float2bfloat16_rn(e);
+      const __nv_bfloat16 lo = __float2bfloat16_rn(e - __bfloat162float(hi));
+      __nv_bfloat16 *row = reinterpret_cast<__nv_bfloat16 *>(A.pe) + (size_t)v * (2 * CCSP_H);
+      row[tid] = hi;
+      row[CCSP_H + tid] = lo;
+    }
   }
 }
 
@@ -288,6 +308,8 @@ __device__ __forceinline__ void simt_gemm_tile(const RowSrc &rs, int m0, const f
 // concatenation:
 //   EPI_STATIC : S[e,:]  = W_c[:, static cols] @ [ (grasp_i) ; geom_i ; geom_j ] + b_c         (plan build)
 //   EPI_L1     : H[e,:]  = SiLU( W_c[:, pose cols] @ [pose_i ; pose_j] + S[e,:] + tb[t,c,:] )  (every call)
+// S lives in the blocked layout of common.cuh::blk_off (shared with the tensor-core epilogue); H of this
+// FP32 path is plain row-major.
 // grid (E'/64, 4); tile_type[row/128] selects the weight block.
 enum { EPI_STATIC = 0, EPI_L1 = 1 };
 
@@ -316,8 +338,10 @@ k_edge_l1_simt(RowSrc rs, const float *__restrict__ Wt /*[C][K][512]*/, const in
       if (EPI == EPI_STATIC) {
         float4 bb = __ldg(reinterpret_cast<const float4 *>(bias + (size_t)c * CCSP_H2 + col));
         v[0] += bb.x; v[1] += bb.y; v[2] += bb.z; v[3] += bb.w;
+        *reinterpret_cast<float4 *>(out + blk_off(row, col)) = make_float4(v[0], v[1], v[2], v[3]);
+        continue;
       } else {
-        float4 s4 = __ldg(reinterpret_cast<const float4 *>(S + row * CCSP_H2 + col));
+        float4 s4 = __ldg(reinterpret_cast<const float4 *>(S + blk_off(row, col)));
         float4 t4 = __ldg(reinterpret_cast<const float4 *>(tb + (size_t)c * CCSP_H2 + col));
         v[0] = silu_f(v[0] + s4.x + t4.x);
         v[1] = silu_f(v[1] + s4.y + t4.y);

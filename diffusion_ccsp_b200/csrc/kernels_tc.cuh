@@ -1,20 +1,27 @@
 // kernels_tc.cuh — tcgen05 (5th-gen tensor core) kernels for the two dense per-edge layers.
 //
-// One persistent, warp-specialised GEMM kernel template, C[256 x NTILE] tiles with FP32 accumulators in
-// TMEM, operands staged in shared memory in the canonical K-major SWIZZLE_64B layout:
+//   k_edge_l1_tc   H = SiLU( [pe_i ; pe_j] W_c,pose^T + S + tb[t,c] )      128 edges x 256 outputs per tile, K = 512
+//   k_edge_dec_tc  o = SiLU( H_half Wd1^T + bd1 ) Wd2^T + bd2               128 (edge,slot) rows x 128, K = 256
 //
-//   warps 0-7   epilogue   tcgen05.ld accumulator -> registers -> fused epilogue -> global
-//   warps 8-11  A producer gather pose-embedding rows through the edge index (16 B loads from L2),
-//                          split FP32 -> (hi, lo) operand pair, st.shared into the swizzled layout
-//   warp  12    B loader   weights are pre-split / pre-swizzled per k-chunk on the host, one
-//                          cp.async.bulk (TMA engine, no tensor map needed) per stage
-//   warp  13    MMA issuer tcgen05.mma (one elected lane), tcgen05.commit -> mbarriers; owns TMEM alloc
+// Both are persistent, warp-specialised kernels with FP32 accumulators in TMEM and operands staged in
+// shared memory in the canonical K-major SWIZZLE_64B layout.  Every operand reaches shared memory by an
+// asynchronous copy of data that is ALREADY in operand format — the conversions happen where the data
+// is produced:
+//   * pose embeddings are written split (hi | lo) by the node kernel; the first-layer A tile is a
+//     16-byte-granular cp.async gather through the edge index straight into the swizzled stage;
+//   * the first-layer epilogue writes H split and pre-swizzled per k-chunk, so the decoder's A tile is
+//     one contiguous cp.async.bulk (TMA engine) per stage;
+//   * weights are split / swizzled per k-chunk on the host once (pack_b_blob), one cp.async.bulk each.
 //
-// FP32 fidelity: the reference computes these layers in true FP32 (cuBLAS/oneDNN sgemm).  The tensor
-// cores take TF32/BF16 operands, so every FP32 operand x is split as x = hi + lo (+ residual) and
-//   A.B ~= A_lo.B_hi + A_hi.B_lo + A_hi.B_hi            (3 MMAs, FP32 accumulation in TMEM)
-// which recovers ~22 (TF32x3) / ~16 (BF16x3) mantissa bits per operand; single-pass modes are kept as
-// explicitly lower-precision options (include/ccsp_b200.h CcspMath).
+//   warps 0-7   epilogue    tcgen05.ld accumulator -> registers -> fused epilogue -> global (coalesced)
+//   warps 8-11  A gather    (first layer only) cp.async 16 B pieces, 2 chunks in flight per thread
+//   next warp   bulk loader one elected lane: cp.async.bulk of B (and A for the decoder) + expect_tx
+//   next warp   MMA issuer  one elected lane: tcgen05.mma / tcgen05.commit -> mbarriers; owns TMEM
+//
+// FP32 fidelity: the reference computes these layers in true FP32.  Tensor cores take TF32/BF16
+// operands, so every FP32 operand x is split as x = hi + lo (+ residual) and
+//   A.B ~= A_lo.B_hi + A_hi.B_lo + A_hi.B_hi            (3 MMAs, FP32 accumulation in TMEM);
+// single-pass modes are kept as explicitly lower-precision options (include/ccsp_b200.h CcspMath).
 #pragma once
 #include <cuda_bf16.h>
 
@@ -24,13 +31,12 @@ namespace ccsp {
 namespace tc {
 
 enum { KIND_TF32 = 0, KIND_BF16 = 1 };
-enum { EPI_TC_L1 = 0, EPI_TC_DEC = 1 };
 
-constexpr int ROWB = 64;        // bytes of K per operand row per stage (SWIZZLE_64B span)
-constexpr int SUB_M = 128;      // rows per tcgen05.mma (one TMEM accumulator = 128 lanes)
-constexpr int NUM_EPI_WARPS = 8, NUM_PROD_WARPS = 4;
-constexpr int WARP_PROD0 = NUM_EPI_WARPS, WARP_BLOAD = WARP_PROD0 + NUM_PROD_WARPS, WARP_MMA = WARP_BLOAD + 1;
-constexpr int NUM_THREADS = (WARP_MMA + 1) * 32;   // 448
+constexpr int ROWB = 64;                 // bytes of K per operand row per stage (SWIZZLE_64B span)
+constexpr int SUB_M = 128;               // rows per tile = TMEM lanes of one accumulator
+constexpr int PART = SUB_M * ROWB;       // bytes of one operand part (hi or lo) of an A stage: 8 KB
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int EPI_THREADS = NUM_EPI_WARPS * 32;
 constexpr uint32_t SPIN_LIMIT = 1u << 27;   // bounded spin: a protocol bug traps instead of hanging the GPU
 
 // ---------------------------------------------------------------------------------------------------
@@ -67,10 +73,16 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint64_t *bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 __device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
@@ -96,16 +108,13 @@ __device__ __forceinline__ void umma_commit(uint64_t *bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-__device__ __forceinline__ void sts128(uint32_t saddr, const uint4 &v) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
 __device__ __forceinline__ float4 ldg_nc_f4(const float4 *p) {
   float4 v;
   asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
   return v;
 }
-// SiLU with the hardware exp2/rcp approximations (abs error < 3e-7 |silu(x)| + 1e-7);
-// the FP32 validation path keeps the libm-accurate version (common.cuh silu_f).
+// SiLU with the hardware exp2/rcp approximations (|error| <~ 3e-7 |silu(x)| + 1e-7; measured parity impact
+// nil); the FP32 validation path keeps the libm-accurate version (common.cuh silu_f).
 __device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
 // 32 lanes x 32 consecutive FP32 columns: thread i of the warp gets lane (lane_base + i), columns col..col+31
@@ -131,7 +140,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
 __device__ __forceinline__ uint64_t smem_desc_sw64(uint32_t saddr) {
   return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (4ull << 61);
 }
-// byte offset of 16-byte chunk `q` (0..3) of row `r` inside a SWIZZLE_64B operand tile (Swizzle<2,4,3>)
+// byte offset of 16-byte piece `q` (0..3) of row `r` inside a SWIZZLE_64B operand tile (Swizzle<2,4,3>)
 __host__ __device__ __forceinline__ uint32_t sw64_off(uint32_t r, uint32_t q) { return r * ROWB + ((q ^ ((r >> 1) & 3)) << 4); }
 
 // FP32 -> operand-pair splits
@@ -146,328 +155,268 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Tile shape: one CTA tile = 256 operand rows (two 128-row sub-tiles = two TMEM accumulators) x NTILE
-// output columns.  Both sub-tiles share every B (weight) stage, which halves the L2->SM weight traffic
-// per FLOP relative to a 128-row tile — the resource that bounds this kernel.
+// arithmetic mode
 // ---------------------------------------------------------------------------------------------------
-template <int KIND_, int NSPLIT_, int NTILE_, int EPI_>
-struct Cfg {
-  static constexpr int KIND = KIND_, NSPLIT = NSPLIT_, NTILE = NTILE_, EPI = EPI_;
+template <int KIND_, int NSPLIT_>
+struct Mode {
+  static constexpr int KIND = KIND_, NSPLIT = NSPLIT_;
   static constexpr int ELT = KIND == KIND_TF32 ? 4 : 2;      // operand element bytes
   static constexpr int KC = ROWB / ELT;                      // K elements per stage (16 / 32)
-  static constexpr int UMMA_K = 32 / ELT;                    // K per tcgen05.mma (8 / 16)
-  static constexpr int KSTEPS = KC / UMMA_K;                 // 2
-  static constexpr int NS = NSPLIT == 3 ? 2 : 1;             // operand copies per stage (hi[, lo])
-  static constexpr int SUB = 2;                              // 128-row sub-tiles per CTA tile
-  static constexpr int TILE_ROWS = SUB * SUB_M;              // 256
-  static constexpr int A_PART = SUB_M * ROWB;                // 8 KB
-  static constexpr int A_SUB = NS * A_PART;
-  static constexpr int A_STAGE = SUB * A_SUB;
-  static constexpr int B_PART = NTILE * ROWB;
-  static constexpr int B_STAGE = NS * B_PART;
-  static constexpr int STAGE = A_STAGE + B_STAGE;
-  static constexpr int NSTAGE = STAGE <= 48 * 1024 ? 4 : 3;  // smem ring depth
-  static constexpr int ACC_COLS = SUB * NTILE;               // TMEM columns per tile
-  static constexpr int NBUF = 512 / ACC_COLS;                // accumulator buffers (1 or 2)
-  static constexpr int TMEM_COLS = 512;
-  static constexpr int SMEM_EXTRA = 8192;                    // barriers, tmem ptr, epilogue constants
-  static constexpr int SMEM_BYTES = NSTAGE * STAGE + SMEM_EXTRA + 1024;   // + alignment slack
-  static constexpr uint32_t IDESC = (1u << 4) | ((KIND == KIND_TF32 ? 2u : 1u) << 7) | ((KIND == KIND_TF32 ? 2u : 1u) << 10) |
-                                    ((uint32_t)(NTILE >> 3) << 17) | ((uint32_t)(SUB_M >> 4) << 24);
-  static_assert(NBUF >= 1 && SMEM_BYTES <= 227 * 1024, "tile does not fit");
+  static constexpr int KSTEPS = 2;                           // tcgen05.mma K (8 / 16 elements = 32 B) per stage
+  static constexpr int NS = NSPLIT == 3 ? 2 : 1;             // operand parts per stage (hi[, lo])
+  static constexpr int A_STAGE = NS * PART;
+  // split pose embedding row written by the node kernel: [256 hi][256 lo] operand elements
+  static constexpr int PE_LO_OFF = CCSP_H * ELT;
+  static constexpr int PE_ROW_BYTES = 2 * CCSP_H * ELT;
+  static constexpr int NKC1 = CCSP_H2 / KC;                  // first layer: K = 512
+  static constexpr int NKC2 = CCSP_H / KC;                   // decoder:     K = 256
+  // bytes of H (operand format) per 128-row x 256-K decoder tile
+  static constexpr size_t H_TILE_BYTES = (size_t)NKC2 * A_STAGE;
+  __host__ __device__ static constexpr uint32_t idesc(int n) {
+    return (1u << 4) | ((KIND == KIND_TF32 ? 2u : 1u) << 7) | ((KIND == KIND_TF32 ? 2u : 1u) << 10) |
+           ((uint32_t)(n >> 3) << 17) | ((uint32_t)(SUB_M >> 4) << 24);
+  }
 };
 
-struct GemmArgs {
-  // A operand: rows of `nseg` 256-float segments, each gathered through an index array or dense
-  const float *a_src[2];
-  const int *a_idx[2];
-  int nseg;
-  // B operand: host-packed stage blobs [group][n_tile][k-chunk][B_STAGE bytes]
-  const uint8_t *b_blob;
-  const int *tile_type;      // weight group per 256-row tile (nullptr -> group 0)
-  int num_m_tiles, n_tiles;  // 256-row tiles, NTILE-column tiles
-  // EPI_TC_L1: H[row, nt*NTILE + j] = SiLU(acc + S[row, .] + tb[group, .])
-  const float *S, *tb;
-  float *H;
-  // EPI_TC_DEC: d = SiLU(acc + bd1); o[row, p] = sum_j d_j Wd2[p, j] + bd2[p]
-  const float *bd1, *Wd2, *bd2;
-  int P;
-  float *o;
-  // performance ablations for the harness (results are garbage when non-zero):
-  //   1 = producers skip the gather/convert/store, 2 = B loader skips the bulk copy,
-  //   4 = epilogue skips global loads/stores, 8 = MMA warp skips the tcgen05.mma instructions
-  int dbg;
+// one k-chunk of MMAs: D[128 x N] (+)= A_stage . B_stage^T
+template <class M, int NTILE>
+__device__ __forceinline__ void issue_chunk(uint32_t d_tmem, uint32_t a_hi, uint32_t b_hi, bool first) {
+  const uint32_t a_lo = a_hi + PART, b_lo = b_hi + NTILE * ROWB;
+#pragma unroll
+  for (int ks = 0; ks < M::KSTEPS; ++ks) {
+    const uint32_t ko = ks * 32;
+    if (M::NSPLIT == 3) {
+      umma<M::KIND>(d_tmem, smem_desc_sw64(a_lo + ko), smem_desc_sw64(b_hi + ko), M::idesc(NTILE), !(first && ks == 0));
+      umma<M::KIND>(d_tmem, smem_desc_sw64(a_hi + ko), smem_desc_sw64(b_lo + ko), M::idesc(NTILE), 1);
+      umma<M::KIND>(d_tmem, smem_desc_sw64(a_hi + ko), smem_desc_sw64(b_hi + ko), M::idesc(NTILE), 1);
+    } else {
+      umma<M::KIND>(d_tmem, smem_desc_sw64(a_hi + ko), smem_desc_sw64(b_hi + ko), M::idesc(NTILE), !(first && ks == 0));
+    }
+  }
+}
+
+// store 32 consecutive FP32 values of one row as operand pieces (hi[, lo]) into a SWIZZLE_64B tile image
+//   TF32: two k-chunks of 16 values;  BF16: one k-chunk of 32 values.  `base` points at the first k-chunk,
+//   `chunk_stride` is the byte distance between consecutive k-chunks (A_STAGE).
+template <class M>
+__device__ __forceinline__ void store_split32(uint8_t *base, size_t chunk_stride, int r, const float *h) {
+  if (M::KIND == KIND_TF32) {
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float *f = h + c * 16 + q * 4;
+        uint4 hi;
+        hi.x = tf32_rna(f[0]); hi.y = tf32_rna(f[1]); hi.z = tf32_rna(f[2]); hi.w = tf32_rna(f[3]);
+        uint8_t *dst = base + c * chunk_stride + sw64_off(r, q);
+        *reinterpret_cast<uint4 *>(dst) = hi;
+        if (M::NS == 2) {
+          uint4 lo;
+          lo.x = tf32_rna(f[0] - __uint_as_float(hi.x)); lo.y = tf32_rna(f[1] - __uint_as_float(hi.y));
+          lo.z = tf32_rna(f[2] - __uint_as_float(hi.z)); lo.w = tf32_rna(f[3] - __uint_as_float(hi.w));
+          *reinterpret_cast<uint4 *>(dst + PART) = lo;
+        }
+      }
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float *f = h + q * 8;
+      float g[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) g[i] = __bfloat162float(__float2bfloat16_rn(f[i]));
+      uint4 hi;
+      hi.x = pack_bf16(g[0], g[1]); hi.y = pack_bf16(g[2], g[3]); hi.z = pack_bf16(g[4], g[5]); hi.w = pack_bf16(g[6], g[7]);
+      uint8_t *dst = base + sw64_off(r, q);
+      *reinterpret_cast<uint4 *>(dst) = hi;
+      if (M::NS == 2) {
+        uint4 lo;
+        lo.x = pack_bf16(f[0] - g[0], f[1] - g[1]); lo.y = pack_bf16(f[2] - g[2], f[3] - g[3]);
+        lo.z = pack_bf16(f[4] - g[4], f[5] - g[5]); lo.w = pack_bf16(f[6] - g[6], f[7] - g[7]);
+        *reinterpret_cast<uint4 *>(dst + PART) = lo;
+      }
+    }
+  }
+}
+
+// ===================================================================================================
+// first layer
+// ===================================================================================================
+struct L1Args {
+  const uint8_t *pe_split;   // [(n+1)][PE_ROW_BYTES] split pose embeddings (row n = zeros)
+  const int *src_i, *src_j;  // [Epad] edge endpoints (padded rows -> n)
+  const uint8_t *b_blob;     // [C][2][NKC1][B_STAGE] packed pose-column weights
+  const int *tile_type;      // [Epad/128] constraint type per tile
+  int num_m_tiles;
+  const float *S;            // static term, blocked layout (common.cuh blk_off)
+  const float *tb;           // [C][512] time term at the current timestep
+  uint8_t *H;                // operand-format activations: [tile][slot][NKC2][NS][PART]
+  int dbg;                   // harness ablations: 1 no A gather, 2 no B copy, 4 no epilogue IO, 8 no MMA
 };
 
-template <class C>
-__global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const GemmArgs A) {
+template <class M>
+struct L1Cfg {
+  static constexpr int NTILE = 256;
+  static constexpr int B_STAGE = M::NS * NTILE * ROWB;
+  static constexpr int STAGE = M::A_STAGE + B_STAGE;
+  static constexpr int NSTAGE = 4;
+  static constexpr int LAG = 2;                              // cp.async chunks in flight per producer thread
+  static constexpr int NBUF = 2;                             // TMEM accumulator buffers (2 x 256 columns)
+  static constexpr int WARP_PROD0 = NUM_EPI_WARPS, NUM_PROD_WARPS = 4;
+  static constexpr int WARP_LOAD = WARP_PROD0 + NUM_PROD_WARPS, WARP_MMA = WARP_LOAD + 1;
+  static constexpr int THREADS = (WARP_MMA + 1) * 32;        // 448
+  static constexpr int SMEM_EXTRA = 2048;
+  static constexpr int SMEM_BYTES = NSTAGE * STAGE + SMEM_EXTRA + 1024;
+};
+
+template <class M>
+__global__ void __launch_bounds__(L1Cfg<M>::THREADS, 1) k_edge_l1_tc(const L1Args A) {
+  using C = L1Cfg<M>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t *extra = smem + C::NSTAGE * C::STAGE;
   uint64_t *full_bar = reinterpret_cast<uint64_t *>(extra);            // [NSTAGE]
-  uint64_t *empty_bar = full_bar + 4;                                  // [NSTAGE]
-  uint64_t *tfull_bar = empty_bar + 4;                                 // [NBUF]
-  uint64_t *tempty_bar = tfull_bar + 2;                                // [NBUF]
-  uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(tempty_bar + 2);
-  float *epi_const = reinterpret_cast<float *>(extra + 256);           // L1: tb slice [NTILE]; DEC: bd1[128] + w2t[128*8] + bd2[8]
+  uint64_t *empty_bar = full_bar + 8;                                  // [NSTAGE]
+  uint64_t *tfull_bar = empty_bar + 8;                                 // [NBUF]
+  uint64_t *tempty_bar = tfull_bar + 4;                                // [NBUF]
+  uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(tempty_bar + 4);
+  float *tb_s = reinterpret_cast<float *>(extra + 512);                // [256] time-term slice of the current tile
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int NKC = A.nseg * CCSP_H / C::KC;
-  const int num_tiles = A.num_m_tiles * A.n_tiles;
+  const int num_tiles = A.num_m_tiles * 2;                             // (128-edge tile, slot)
+  const uint32_t smem_base = smem_u32(smem);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < C::NSTAGE; ++s) { mbar_init(&full_bar[s], 32 + 1); mbar_init(&empty_bar[s], 1); }
-    for (int b = 0; b < C::NBUF; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], NUM_EPI_WARPS * 32); }
+    for (int s = 0; s < C::NSTAGE; ++s) { mbar_init(&full_bar[s], C::NUM_PROD_WARPS * 32 + 1); mbar_init(&empty_bar[s], 1); }
+    for (int b = 0; b < C::NBUF; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], EPI_THREADS); }
     fence_barrier_init();
   }
-  if (warp == WARP_MMA) tmem_alloc(tmem_ptr, C::TMEM_COLS);
-  if (C::EPI == EPI_TC_DEC && warp < NUM_EPI_WARPS) {
-    const int nth = NUM_EPI_WARPS * 32;
-    for (int i = threadIdx.x; i < CCSP_HH; i += nth) epi_const[i] = A.bd1[i];
-    for (int i = threadIdx.x; i < CCSP_MAXP * CCSP_HH; i += nth) {      // w2t[j][p], zero-padded to 8 outputs
-      const int j = i / CCSP_MAXP, pp = i % CCSP_MAXP;
-      epi_const[CCSP_HH + i] = pp < A.P ? A.Wd2[pp * CCSP_HH + j] : 0.f;
-    }
-    for (int i = threadIdx.x; i < CCSP_MAXP; i += nth) epi_const[CCSP_HH + CCSP_MAXP * CCSP_HH + i] = i < A.P ? A.bd2[i] : 0.f;
-  }
+  if (warp == C::WARP_MMA) tmem_alloc(tmem_ptr, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  if (warp >= WARP_PROD0 && warp < WARP_PROD0 + C::NSTAGE) {
-    // ================================ A producers ================================================
-    // producer warp pw OWNS ring stage pw and converts k-chunks kc == pw (mod NSTAGE): 256 rows x 64 B of
-    // operand per chunk.  One owner per stage keeps every waiter at most one mbarrier phase ahead (parity
-    // waits cannot tell phases two apart); with a 3-deep ring the 4th producer warp stays idle.
-    const int pw = warp - WARP_PROD0;
-    const uint32_t smem_base = smem_u32(smem);
-    const int q = lane & 3, r0 = lane >> 2;
-    uint32_t tile_iter = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_iter) {
-      const int m0 = (tile / A.n_tiles) * C::TILE_ROWS;
-      int cur_seg = -1;
-      uint32_t rowoff[32];
-      const int kc_first = (pw + C::NSTAGE - (int)((tile_iter * (uint32_t)NKC) % C::NSTAGE)) % C::NSTAGE;
-      for (int kc = kc_first; kc < NKC; kc += C::NSTAGE) {
-        const uint32_t g = tile_iter * NKC + kc;             // global chunk counter; g % NSTAGE == pw
-        const uint32_t s = pw;
-        const int k0 = kc * C::KC;
-        const int seg = k0 >> 8;
-        if (seg != cur_seg) {
-          cur_seg = seg;
+  if (warp >= C::WARP_PROD0 && warp < C::WARP_LOAD) {
+    // ============ A gather: 128 threads, thread = (piece q, rows r0 + 32 p); cp.async, LAG chunks in flight
+    const int t = threadIdx.x - C::WARP_PROD0 * 32;
+    const int q = t & 3, r0 = t >> 2;
+    uint32_t g = 0;                      // global chunk counter (issue side)
+    uint32_t sig = 0;                    // chunks already signalled full
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile >> 1) * SUB_M;
+      size_t roff[4];
+#pragma unroll 1
+      for (int kc = 0; kc < M::NKC1; ++kc, ++g) {
+        if (kc == 0 || kc == M::NKC1 / 2) {
+          const int *idx = kc == 0 ? A.src_i : A.src_j;
 #pragma unroll
-          for (int p = 0; p < 32; ++p) {
-            const int row = m0 + p * 8 + r0;
-            rowoff[p] = (uint32_t)(A.a_idx[seg] ? __ldg(&A.a_idx[seg][row]) : row) * CCSP_H;
-          }
+          for (int p = 0; p < 4; ++p) roff[p] = (size_t)__ldg(&idx[m0 + r0 + 32 * p]) * M::PE_ROW_BYTES;
         }
-        const float *src = A.a_src[seg] + (k0 & (CCSP_H - 1));
-        const uint32_t stA = smem_base + s * C::STAGE;
+        const uint32_t s = g % C::NSTAGE;
         mbar_wait(&empty_bar[s], ((g / C::NSTAGE) & 1) ^ 1);
-        if (A.dbg & 1) {
-          mbar_arrive(&full_bar[s]);
-          continue;
-        }
-        if (C::KIND == KIND_TF32) {
+        if (!(A.dbg & 1)) {
+          const uint32_t koff = (uint32_t)(kc % (M::NKC1 / 2)) * ROWB + q * 16;
+          const uint32_t st = smem_base + s * C::STAGE;
 #pragma unroll
-          for (int hb = 0; hb < 2; ++hb) {                 // two batches of 16 rows-in-flight per lane
-            float4 v[16];
-#pragma unroll
-            for (int p = 0; p < 16; ++p) v[p] = __ldg(reinterpret_cast<const float4 *>(src + rowoff[hb * 16 + p] + q * 4));
-#pragma unroll
-            for (int p = 0; p < 16; ++p) {
-              const int r = (hb * 16 + p) * 8 + r0;          // row within the 256-row tile
-              const uint32_t dst = stA + (r >> 7) * C::A_SUB + sw64_off(r & 127, q);
-              uint4 hi;
-              hi.x = tf32_rna(v[p].x); hi.y = tf32_rna(v[p].y); hi.z = tf32_rna(v[p].z); hi.w = tf32_rna(v[p].w);
-              sts128(dst, hi);
-              if (C::NS == 2) {
-                uint4 lo;
-                lo.x = tf32_rna(v[p].x - __uint_as_float(hi.x)); lo.y = tf32_rna(v[p].y - __uint_as_float(hi.y));
-                lo.z = tf32_rna(v[p].z - __uint_as_float(hi.z)); lo.w = tf32_rna(v[p].w - __uint_as_float(hi.w));
-                sts128(dst + C::A_PART, lo);
-              }
-            }
-          }
-        } else {
-#pragma unroll
-          for (int hb = 0; hb < 4; ++hb) {                 // four batches of 8 rows (2 float4 each) per lane
-            float4 v[16];
-#pragma unroll
-            for (int p = 0; p < 8; ++p) {
-              const float *sp = src + rowoff[hb * 8 + p] + q * 8;
-              v[2 * p] = __ldg(reinterpret_cast<const float4 *>(sp));
-              v[2 * p + 1] = __ldg(reinterpret_cast<const float4 *>(sp + 4));
-            }
-#pragma unroll
-            for (int p = 0; p < 8; ++p) {
-              const int r = (hb * 8 + p) * 8 + r0;
-              const uint32_t dst = stA + (r >> 7) * C::A_SUB + sw64_off(r & 127, q);
-              const float f[8] = {v[2 * p].x, v[2 * p].y, v[2 * p].z, v[2 * p].w, v[2 * p + 1].x, v[2 * p + 1].y, v[2 * p + 1].z, v[2 * p + 1].w};
-              float h[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) h[i] = __bfloat162float(__float2bfloat16_rn(f[i]));
-              uint4 hi;
-              hi.x = pack_bf16(h[0], h[1]); hi.y = pack_bf16(h[2], h[3]); hi.z = pack_bf16(h[4], h[5]); hi.w = pack_bf16(h[6], h[7]);
-              sts128(dst, hi);
-              if (C::NS == 2) {
-                uint4 lo;
-                lo.x = pack_bf16(f[0] - h[0], f[1] - h[1]); lo.y = pack_bf16(f[2] - h[2], f[3] - h[3]);
-                lo.z = pack_bf16(f[4] - h[4], f[5] - h[5]); lo.w = pack_bf16(f[6] - h[6], f[7] - h[7]);
-                sts128(dst + C::A_PART, lo);
-              }
-            }
+          for (int p = 0; p < 4; ++p) {
+            const uint8_t *src = A.pe_split + roff[p] + koff;
+            const uint32_t dst = st + sw64_off(r0 + 32 * p, q);
+            cp_async16(dst, src);
+            if (M::NS == 2) cp_async16(dst + PART, src + M::PE_LO_OFF);
           }
         }
-        fence_proxy_async();
-        mbar_arrive(&full_bar[s]);
+        cp_async_commit();
+        if (g - sig >= (uint32_t)C::LAG) {         // chunk `sig` has landed: publish it to the async proxy
+          cp_async_wait<C::LAG>();
+          fence_proxy_async();
+          mbar_arrive(&full_bar[sig % C::NSTAGE]);
+          ++sig;
+        }
       }
     }
-  } else if (warp == WARP_BLOAD) {
-    // ================================ B loader ==================================================
+    cp_async_wait<0>();
+    fence_proxy_async();
+    for (; sig < g; ++sig) mbar_arrive(&full_bar[sig % C::NSTAGE]);
+  } else if (warp == C::WARP_LOAD) {
+    // ============ B loader ======================================================================
     if (lane == 0) {
       uint32_t g = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int mt = tile / A.n_tiles, nt = tile % A.n_tiles;
-        const int grp = A.tile_type ? __ldg(&A.tile_type[mt]) : 0;
-        const uint8_t *blob = A.b_blob + ((size_t)(grp * A.n_tiles + nt) * NKC) * C::B_STAGE;
-        for (int kc = 0; kc < NKC; ++kc, ++g) {
+        const int grp = __ldg(&A.tile_type[tile >> 1]);
+        const uint8_t *blob = A.b_blob + ((size_t)(grp * 2 + (tile & 1)) * M::NKC1) * C::B_STAGE;
+        for (int kc = 0; kc < M::NKC1; ++kc, ++g) {
           const uint32_t s = g % C::NSTAGE;
           mbar_wait(&empty_bar[s], ((g / C::NSTAGE) & 1) ^ 1);
-          if (A.dbg & 2) {
-            mbar_arrive(&full_bar[s]);
-            continue;
-          }
+          if (A.dbg & 2) { mbar_arrive(&full_bar[s]); continue; }
           mbar_arrive_expect_tx(&full_bar[s], C::B_STAGE);
-          bulk_g2s(smem + s * C::STAGE + C::A_STAGE, blob + (size_t)kc * C::B_STAGE, C::B_STAGE, &full_bar[s]);
+          bulk_g2s(smem_base + s * C::STAGE + M::A_STAGE, blob + (size_t)kc * C::B_STAGE, C::B_STAGE, &full_bar[s]);
         }
       }
     }
-  } else if (warp == WARP_MMA) {
-    // ================================ MMA issuer ================================================
+  } else if (warp == C::WARP_MMA) {
+    // ============ MMA issuer ====================================================================
     if (lane == 0) {
       uint32_t g = 0, tcount = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
         const uint32_t buf = tcount % C::NBUF;
         mbar_wait(&tempty_bar[buf], ((tcount / C::NBUF) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + buf * C::ACC_COLS;
-        for (int kc = 0; kc < NKC; ++kc, ++g) {
+        const uint32_t d_tmem = tmem_base + buf * C::NTILE;
+        for (int kc = 0; kc < M::NKC1; ++kc, ++g) {
           const uint32_t s = g % C::NSTAGE;
           mbar_wait(&full_bar[s], (g / C::NSTAGE) & 1);
           tc_fence_after();
-          const uint32_t a0 = smem_u32(smem + s * C::STAGE);
-          const uint32_t b_hi = a0 + C::A_STAGE, b_lo = b_hi + C::B_PART;
-#pragma unroll
-          for (int ks = 0; ks < ((A.dbg & 8) ? 0 : C::KSTEPS); ++ks) {
-            const uint32_t ko = ks * 32;
-#pragma unroll
-            for (int sub = 0; sub < C::SUB; ++sub) {
-              const uint32_t a_hi = a0 + sub * C::A_SUB, a_lo = a_hi + C::A_PART;
-              const uint32_t d = d_tmem + sub * C::NTILE;
-              if (C::NSPLIT == 3) {
-                umma<C::KIND>(d, smem_desc_sw64(a_lo + ko), smem_desc_sw64(b_hi + ko), C::IDESC, (kc | ks) != 0);
-                umma<C::KIND>(d, smem_desc_sw64(a_hi + ko), smem_desc_sw64(b_lo + ko), C::IDESC, 1);
-                umma<C::KIND>(d, smem_desc_sw64(a_hi + ko), smem_desc_sw64(b_hi + ko), C::IDESC, 1);
-              } else {
-                umma<C::KIND>(d, smem_desc_sw64(a_hi + ko), smem_desc_sw64(b_hi + ko), C::IDESC, (kc | ks) != 0);
-              }
-            }
-          }
+          const uint32_t a_hi = smem_base + s * C::STAGE;
+          if (!(A.dbg & 8)) issue_chunk<M, C::NTILE>(d_tmem, a_hi, a_hi + M::A_STAGE, kc == 0);
           umma_commit(&empty_bar[s]);        // frees the smem stage once these MMAs have read it
         }
-        umma_commit(&tfull_bar[buf]);        // accumulators complete -> epilogue
+        umma_commit(&tfull_bar[buf]);        // accumulator complete -> epilogue
       }
     }
   } else if (warp < NUM_EPI_WARPS) {
-    // ============== epilogue: warp w <-> sub-tile (w >> 2), TMEM lanes 32 (w & 3) .. +31 ==========
+    // ============ epilogue: warp w <-> TMEM lanes 32 (w & 3).., columns 128 (w >> 2).. +127 ========
     uint32_t tcount = 0;
-    const int quarter = warp & 3, sub = warp >> 2;
+    const int quarter = warp & 3, chalf = warp >> 2;
+    const int r = quarter * 32 + lane;                                  // row within the tile
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
       const uint32_t buf = tcount % C::NBUF;
-      const int mt = tile / A.n_tiles, nt = tile % A.n_tiles;
-      const size_t row = (size_t)mt * C::TILE_ROWS + sub * SUB_M + quarter * 32 + lane;
-      const uint32_t taddr = tmem_base + buf * C::ACC_COLS + sub * C::NTILE + ((uint32_t)(quarter * 32) << 16);
-      if (C::EPI == EPI_TC_L1) {
-        const int grp = A.tile_type ? __ldg(&A.tile_type[mt]) : 0;
-        const float4 *Sv = reinterpret_cast<const float4 *>(A.S + row * CCSP_H2 + nt * C::NTILE);
-        float4 *Hv = reinterpret_cast<float4 *>(A.H + row * CCSP_H2 + nt * C::NTILE);
-        float4 sn[8];                                       // static term, prefetched one 32-column chunk ahead
+      const int mt = tile >> 1, slot = tile & 1;
+      const int grp = __ldg(&A.tile_type[mt]);
+      const size_t row = (size_t)mt * SUB_M + r;
+      const int col0 = slot * 256 + chalf * 128;                        // first of this thread's 128 columns
+      // S in the blocked layout: 32-row x 32-col blocks of 8 pieces x 32 lanes x 16 B  (coalesced 512 B / instr)
+      const float4 *Sblk = reinterpret_cast<const float4 *>(A.S) + (((row >> 5) * 16 + (col0 >> 5)) * 8) * 32 + lane;
+      float4 sn[8];                                                    // prefetched one 32-column chunk ahead
 #pragma unroll
-        for (int qq = 0; qq < 8; ++qq) sn[qq] = (A.dbg & 4) ? make_float4(0.f, 0.f, 0.f, 0.f) : ldg_nc_f4(Sv + qq);
-        asm volatile("bar.sync 1, 256;" ::: "memory");      // previous tile's readers of epi_const are done
-        for (int i = threadIdx.x; i < C::NTILE; i += NUM_EPI_WARPS * 32)
-          epi_const[i] = __ldg(&A.tb[(size_t)grp * CCSP_H2 + nt * C::NTILE + i]);
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        mbar_wait(&tfull_bar[buf], (tcount / C::NBUF) & 1);
-        tc_fence_after();
+      for (int j = 0; j < 8; ++j) sn[j] = (A.dbg & 4) ? make_float4(0.f, 0.f, 0.f, 0.f) : ldg_nc_f4(Sblk + j * 32);
+      asm volatile("bar.sync 1, 256;" ::: "memory");                  // previous tile's readers of tb_s are done
+      tb_s[threadIdx.x] = __ldg(&A.tb[(size_t)grp * CCSP_H2 + slot * 256 + threadIdx.x]);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      mbar_wait(&tfull_bar[buf], (tcount / C::NBUF) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + buf * C::NTILE + chalf * 128 + ((uint32_t)(quarter * 32) << 16);
+      uint8_t *Hrow = A.H + (size_t)tile * M::H_TILE_BYTES + (size_t)(chalf * 128 / M::KC) * M::A_STAGE;
 #pragma unroll 1
-        for (int cb = 0; cb < C::NTILE; cb += 32) {
-          float4 sc[8];
+      for (int cb = 0; cb < 128; cb += 32) {
+        float4 sc[8];
 #pragma unroll
-          for (int qq = 0; qq < 8; ++qq) sc[qq] = sn[qq];
-          if (cb + 32 < C::NTILE && !(A.dbg & 4)) {
+        for (int j = 0; j < 8; ++j) sc[j] = sn[j];
+        if (cb + 32 < 128 && !(A.dbg & 4)) {
 #pragma unroll
-            for (int qq = 0; qq < 8; ++qq) sn[qq] = ldg_nc_f4(Sv + (cb + 32) / 4 + qq);
-          }
-          float v[32];
-          tmem_ld32(taddr + cb, v);
-#pragma unroll
-          for (int qq = 0; qq < 8; ++qq) {
-            const float4 t4 = *reinterpret_cast<const float4 *>(&epi_const[cb + 4 * qq]);
-            float4 o4;
-            o4.x = silu_fast(v[4 * qq] + sc[qq].x + t4.x); o4.y = silu_fast(v[4 * qq + 1] + sc[qq].y + t4.y);
-            o4.z = silu_fast(v[4 * qq + 2] + sc[qq].z + t4.z); o4.w = silu_fast(v[4 * qq + 3] + sc[qq].w + t4.w);
-            if (!(A.dbg & 4) || o4.x == 12345.678f) Hv[cb / 4 + qq] = o4;
-          }
+          for (int j = 0; j < 8; ++j) sn[j] = ldg_nc_f4(Sblk + ((cb + 32) >> 5) * 256 + j * 32);
         }
-      } else {
-        mbar_wait(&tfull_bar[buf], (tcount / C::NBUF) & 1);
-        tc_fence_after();
-        const float *bd1 = epi_const, *w2t = epi_const + CCSP_HH, *bd2 = epi_const + CCSP_HH + CCSP_MAXP * CCSP_HH;
-        if (A.P <= 4) {
-          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 1
-          for (int cb = 0; cb < C::NTILE; cb += 32) {
-            float v[32];
-            tmem_ld32(taddr + cb, v);
+        float v[32];
+        tmem_ld32(taddr + cb, v);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float d = silu_fast(v[j] + bd1[cb + j]);
-              const float4 w = *reinterpret_cast<const float4 *>(&w2t[(cb + j) * CCSP_MAXP]);
-              acc.x = fmaf(d, w.x, acc.x); acc.y = fmaf(d, w.y, acc.y); acc.z = fmaf(d, w.z, acc.z); acc.w = fmaf(d, w.w, acc.w);
-            }
-          }
-          const float r4[4] = {acc.x + bd2[0], acc.y + bd2[1], acc.z + bd2[2], acc.w + bd2[3]};
-          if (A.P == 4) {
-            *reinterpret_cast<float4 *>(A.o + row * 4) = make_float4(r4[0], r4[1], r4[2], r4[3]);
-          } else {
-#pragma unroll
-            for (int p = 0; p < 4; ++p)
-              if (p < A.P) A.o[row * A.P + p] = r4[p];
-          }
-        } else {
-          float acc[CCSP_MAXP];
-#pragma unroll
-          for (int p = 0; p < CCSP_MAXP; ++p) acc[p] = 0.f;
-#pragma unroll 1
-          for (int cb = 0; cb < C::NTILE; cb += 32) {
-            float v[32];
-            tmem_ld32(taddr + cb, v);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float d = silu_fast(v[j] + bd1[cb + j]);
-              const float4 w0 = *reinterpret_cast<const float4 *>(&w2t[(cb + j) * CCSP_MAXP]);
-              const float4 w1 = *reinterpret_cast<const float4 *>(&w2t[(cb + j) * CCSP_MAXP + 4]);
-              acc[0] = fmaf(d, w0.x, acc[0]); acc[1] = fmaf(d, w0.y, acc[1]); acc[2] = fmaf(d, w0.z, acc[2]); acc[3] = fmaf(d, w0.w, acc[3]);
-              acc[4] = fmaf(d, w1.x, acc[4]); acc[5] = fmaf(d, w1.y, acc[5]); acc[6] = fmaf(d, w1.z, acc[6]); acc[7] = fmaf(d, w1.w, acc[7]);
-            }
-          }
-#pragma unroll
-          for (int p = 0; p < CCSP_MAXP; ++p)
-            if (p < A.P) A.o[row * A.P + p] = acc[p] + bd2[p];
+        for (int j = 0; j < 8; ++j) {
+          const float4 t4 = *reinterpret_cast<const float4 *>(&tb_s[chalf * 128 + cb + 4 * j]);
+          v[4 * j] = silu_fast(v[4 * j] + sc[j].x + t4.x);
+          v[4 * j + 1] = silu_fast(v[4 * j + 1] + sc[j].y + t4.y);
+          v[4 * j + 2] = silu_fast(v[4 * j + 2] + sc[j].z + t4.z);
+          v[4 * j + 3] = silu_fast(v[4 * j + 3] + sc[j].w + t4.w);
         }
+        if (!(A.dbg & 4)) store_split32<M>(Hrow + (size_t)(cb / M::KC) * M::A_STAGE, M::A_STAGE, r, v);
       }
       tc_fence_before();
       mbar_arrive(&tempty_bar[buf]);
@@ -475,7 +424,171 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_gemm_tc(const GemmArgs A) {
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == WARP_MMA) tmem_dealloc(tmem_base, C::TMEM_COLS);
+  if (warp == C::WARP_MMA) tmem_dealloc(tmem_base, 512);
+}
+
+// ===================================================================================================
+// decoder
+// ===================================================================================================
+struct DecArgs {
+  const uint8_t *H;          // operand-format activations written by k_edge_l1_tc
+  const uint8_t *b_blob;     // [NKC2][B_STAGE] packed pose_decoder.0 weights
+  int num_tiles;             // (128-edge tile, slot) pairs = 2 * Epad / 128
+  const float *bd1, *Wd2, *bd2;
+  int P;
+  float *o;                  // [Epad][2][P]
+  int dbg;
+};
+
+template <class M>
+struct DecCfg {
+  static constexpr int NTILE = 128;
+  static constexpr int B_STAGE = M::NS * NTILE * ROWB;
+  static constexpr int STAGE = M::A_STAGE + B_STAGE;
+  static constexpr int NSTAGE = 6;
+  static constexpr int NBUF = 4;                             // 4 x 128 TMEM columns
+  static constexpr int WARP_LOAD = NUM_EPI_WARPS, WARP_MMA = WARP_LOAD + 1;
+  static constexpr int THREADS = (WARP_MMA + 1) * 32;        // 320
+  static constexpr int SMEM_EXTRA = 512 + (CCSP_HH + CCSP_MAXP * CCSP_HH + CCSP_MAXP) * 4 + SUB_M * CCSP_MAXP * 4;
+  static constexpr int SMEM_BYTES = NSTAGE * STAGE + SMEM_EXTRA + 1024;
+};
+
+template <class M>
+__global__ void __launch_bounds__(DecCfg<M>::THREADS, 1) k_edge_dec_tc(const DecArgs A) {
+  using C = DecCfg<M>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t *extra = smem + C::NSTAGE * C::STAGE;
+  uint64_t *full_bar = reinterpret_cast<uint64_t *>(extra);            // [NSTAGE]
+  uint64_t *empty_bar = full_bar + 8;
+  uint64_t *tfull_bar = empty_bar + 8;                                 // [NBUF]
+  uint64_t *tempty_bar = tfull_bar + 4;
+  uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(tempty_bar + 4);
+  float *bd1 = reinterpret_cast<float *>(extra + 512);                 // [128]
+  float *w2t = bd1 + CCSP_HH;                                          // [128][8]  (transposed, zero-padded)
+  float *bd2 = w2t + CCSP_MAXP * CCSP_HH;                              // [8]
+  float *red = bd2 + CCSP_MAXP;                                        // [128][8] partial sums of the upper column half
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t smem_base = smem_u32(smem);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C::NSTAGE; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int b = 0; b < C::NBUF; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], EPI_THREADS); }
+    fence_barrier_init();
+  }
+  if (warp == C::WARP_MMA) tmem_alloc(tmem_ptr, 512);
+  if (warp < NUM_EPI_WARPS) {
+    for (int i = threadIdx.x; i < CCSP_HH; i += EPI_THREADS) bd1[i] = A.bd1[i];
+    for (int i = threadIdx.x; i < CCSP_MAXP * CCSP_HH; i += EPI_THREADS) {
+      const int j = i / CCSP_MAXP, pp = i % CCSP_MAXP;
+      w2t[i] = pp < A.P ? A.Wd2[pp * CCSP_HH + j] : 0.f;
+    }
+    if (threadIdx.x < CCSP_MAXP) bd2[threadIdx.x] = threadIdx.x < A.P ? A.bd2[threadIdx.x] : 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == C::WARP_LOAD) {
+    if (lane == 0) {
+      uint32_t g = 0;
+      for (int tile = blockIdx.x; tile < A.num_tiles; tile += gridDim.x) {
+        const uint8_t *a = A.H + (size_t)tile * M::H_TILE_BYTES;
+        for (int kc = 0; kc < M::NKC2; ++kc, ++g) {
+          const uint32_t s = g % C::NSTAGE;
+          mbar_wait(&empty_bar[s], ((g / C::NSTAGE) & 1) ^ 1);
+          if (A.dbg & 3) { mbar_arrive(&full_bar[s]); continue; }
+          mbar_arrive_expect_tx(&full_bar[s], C::STAGE);
+          bulk_g2s(smem_base + s * C::STAGE, a + (size_t)kc * M::A_STAGE, M::A_STAGE, &full_bar[s]);
+          bulk_g2s(smem_base + s * C::STAGE + M::A_STAGE, A.b_blob + (size_t)kc * C::B_STAGE, C::B_STAGE, &full_bar[s]);
+        }
+      }
+    }
+  } else if (warp == C::WARP_MMA) {
+    if (lane == 0) {
+      uint32_t g = 0, tcount = 0;
+      for (int tile = blockIdx.x; tile < A.num_tiles; tile += gridDim.x, ++tcount) {
+        const uint32_t buf = tcount % C::NBUF;
+        mbar_wait(&tempty_bar[buf], ((tcount / C::NBUF) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * C::NTILE;
+        for (int kc = 0; kc < M::NKC2; ++kc, ++g) {
+          const uint32_t s = g % C::NSTAGE;
+          mbar_wait(&full_bar[s], (g / C::NSTAGE) & 1);
+          tc_fence_after();
+          const uint32_t a_hi = smem_base + s * C::STAGE;
+          if (!(A.dbg & 8)) issue_chunk<M, C::NTILE>(d_tmem, a_hi, a_hi + M::A_STAGE, kc == 0);
+          umma_commit(&empty_bar[s]);
+        }
+        umma_commit(&tfull_bar[buf]);
+      }
+    }
+  } else if (warp < NUM_EPI_WARPS) {
+    // warp w <-> TMEM lanes 32 (w & 3).., columns 64 (w >> 2).. +63; the two column halves of a row are
+    // combined through shared memory (fixed order: lower half + upper half) by the lower-half warp.
+    uint32_t tcount = 0;
+    const int quarter = warp & 3, chalf = warp >> 2;
+    const int r = quarter * 32 + lane;
+    for (int tile = blockIdx.x; tile < A.num_tiles; tile += gridDim.x, ++tcount) {
+      const uint32_t buf = tcount % C::NBUF;
+      mbar_wait(&tfull_bar[buf], (tcount / C::NBUF) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + buf * C::NTILE + chalf * 64 + ((uint32_t)(quarter * 32) << 16);
+      float acc[CCSP_MAXP];
+#pragma unroll
+      for (int p = 0; p < CCSP_MAXP; ++p) acc[p] = 0.f;
+#pragma unroll 1
+      for (int cb = 0; cb < 64; cb += 32) {
+        float v[32];
+        tmem_ld32(taddr + cb, v);
+        const int c0 = chalf * 64 + cb;
+        if (A.P <= 4) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float d = silu_fast(v[j] + bd1[c0 + j]);
+            const float4 w = *reinterpret_cast<const float4 *>(&w2t[(c0 + j) * CCSP_MAXP]);
+            acc[0] = fmaf(d, w.x, acc[0]); acc[1] = fmaf(d, w.y, acc[1]); acc[2] = fmaf(d, w.z, acc[2]); acc[3] = fmaf(d, w.w, acc[3]);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float d = silu_fast(v[j] + bd1[c0 + j]);
+            const float4 w0 = *reinterpret_cast<const float4 *>(&w2t[(c0 + j) * CCSP_MAXP]);
+            const float4 w1 = *reinterpret_cast<const float4 *>(&w2t[(c0 + j) * CCSP_MAXP + 4]);
+            acc[0] = fmaf(d, w0.x, acc[0]); acc[1] = fmaf(d, w0.y, acc[1]); acc[2] = fmaf(d, w0.z, acc[2]); acc[3] = fmaf(d, w0.w, acc[3]);
+            acc[4] = fmaf(d, w1.x, acc[4]); acc[5] = fmaf(d, w1.y, acc[5]); acc[6] = fmaf(d, w1.z, acc[6]); acc[7] = fmaf(d, w1.w, acc[7]);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[buf]);                                   // accumulator drained: MMA may reuse it
+      if (chalf == 1) {
+        *reinterpret_cast<float4 *>(&red[r * CCSP_MAXP]) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        if (A.P > 4) *reinterpret_cast<float4 *>(&red[r * CCSP_MAXP + 4]) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+      }
+      asm volatile("bar.sync 2, 256;" ::: "memory");
+      if (chalf == 0 && !(A.dbg & 4)) {
+        const int mt = tile >> 1, slot = tile & 1;
+        float *orow = A.o + ((size_t)(mt * SUB_M + r) * 2 + slot) * A.P;
+        float res[CCSP_MAXP];
+#pragma unroll
+        for (int p = 0; p < CCSP_MAXP; ++p) res[p] = (acc[p] + red[r * CCSP_MAXP + p]) + bd2[p];
+        if (A.P == 4) {
+          *reinterpret_cast<float4 *>(orow) = make_float4(res[0], res[1], res[2], res[3]);
+        } else {
+#pragma unroll
+          for (int p = 0; p < CCSP_MAXP; ++p)
+            if (p < A.P) orow[p] = res[p];
+        }
+      }
+      asm volatile("bar.sync 3, 256;" ::: "memory");                  // `red` may be overwritten by the next tile
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == C::WARP_MMA) tmem_dealloc(tmem_base, 512);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -504,44 +617,59 @@ inline float host_bf16_to_f(uint16_t h) {
   return f;
 }
 
-template <class C>
+template <class M, int NTILE>
 void pack_b_blob(const float *W, int ldw, int k_begin, int K_total, int n_rows_total, uint8_t *out) {
-  const int n_tiles = n_rows_total / C::NTILE, NKC = K_total / C::KC;
-  const int EPC = 16 / C::ELT;   // elements per 16-byte chunk
+  const int n_tiles = n_rows_total / NTILE, NKC = K_total / M::KC;
+  const int EPC = 16 / M::ELT;   // elements per 16-byte piece
+  const int B_PART = NTILE * ROWB, B_STAGE = M::NS * B_PART;
   for (int nt = 0; nt < n_tiles; ++nt)
     for (int kc = 0; kc < NKC; ++kc) {
-      uint8_t *st = out + ((size_t)nt * NKC + kc) * C::B_STAGE;
-      for (int r = 0; r < C::NTILE; ++r)
-        for (int kk = 0; kk < C::KC; ++kk) {
-          const float x = W[(size_t)(nt * C::NTILE + r) * ldw + k_begin + kc * C::KC + kk];
-          const uint32_t off = sw64_off(r, kk / EPC) + (kk % EPC) * C::ELT;
-          if (C::KIND == KIND_TF32) {
+      uint8_t *st = out + ((size_t)nt * NKC + kc) * B_STAGE;
+      for (int r = 0; r < NTILE; ++r)
+        for (int kk = 0; kk < M::KC; ++kk) {
+          const float x = W[(size_t)(nt * NTILE + r) * ldw + k_begin + kc * M::KC + kk];
+          const uint32_t off = sw64_off(r, kk / EPC) + (kk % EPC) * M::ELT;
+          if (M::KIND == KIND_TF32) {
             uint32_t hi = host_tf32_rna(x);
             float hf;
             memcpy(&hf, &hi, 4);
             memcpy(st + off, &hi, 4);
-            if (C::NS == 2) { uint32_t lo = host_tf32_rna(x - hf); memcpy(st + C::B_PART + off, &lo, 4); }
+            if (M::NS == 2) { uint32_t lo = host_tf32_rna(x - hf); memcpy(st + B_PART + off, &lo, 4); }
           } else {
             uint16_t hi = host_bf16_rn(x);
             memcpy(st + off, &hi, 2);
-            if (C::NS == 2) { uint16_t lo = host_bf16_rn(x - host_bf16_to_f(hi)); memcpy(st + C::B_PART + off, &lo, 2); }
+            if (M::NS == 2) { uint16_t lo = host_bf16_rn(x - host_bf16_to_f(hi)); memcpy(st + B_PART + off, &lo, 2); }
           }
         }
     }
 }
 
-template <class C>
-cudaError_t launch_gemm_tc(const GemmArgs &a, int num_sms, cudaStream_t st) {
+template <class M>
+cudaError_t launch_l1_tc(const L1Args &a, int num_sms, cudaStream_t st) {
+  using C = L1Cfg<M>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(k_gemm_tc<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(k_edge_l1_tc<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  const int tiles = a.num_m_tiles * a.n_tiles;
+  const int tiles = a.num_m_tiles * 2;
   if (tiles == 0) return cudaSuccess;
-  const int grid = tiles < num_sms ? tiles : num_sms;
-  k_gemm_tc<C><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(a);
+  k_edge_l1_tc<M><<<tiles < num_sms ? tiles : num_sms, C::THREADS, C::SMEM_BYTES, st>>>(a);
+  return cudaGetLastError();
+}
+
+template <class M>
+cudaError_t launch_dec_tc(const DecArgs &a, int num_sms, cudaStream_t st) {
+  using C = DecCfg<M>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(k_edge_dec_tc<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  if (a.num_tiles == 0) return cudaSuccess;
+  k_edge_dec_tc<M><<<a.num_tiles < num_sms ? a.num_tiles : num_sms, C::THREADS, C::SMEM_BYTES, st>>>(a);
   return cudaGetLastError();
 }
 

@@ -1,11 +1,10 @@
-// tc_gemm_test.cu — standalone numerics + throughput check of the tcgen05 GEMM kernels (kernels_tc.cuh)
-// against a double-precision CPU reference.  Built and run on the B200 box:
-//   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -o tc_gemm_test tc_gemm_test.cu
-//   timeout 120 ./tc_gemm_test [perf]
+// tc_gemm_test.cu — standalone numerics + throughput check of the tcgen05 edge kernels (kernels_tc.cuh)
+// against a double-precision CPU reference.  Built by `python -m diffusion_ccsp_b200.build --tests`, run on
+// the B200 box:   timeout 200 diffusion_ccsp_b200/lib/tc_gemm_test [perf]
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#include <cmath>
 #include <random>
 #include <vector>
 
@@ -19,13 +18,13 @@ void count_launch() {}
 using namespace ccsp;
 using namespace ccsp::tc;
 
-#define CK(x)                                                                              \
-  do {                                                                                     \
-    cudaError_t e_ = (x);                                                                  \
-    if (e_ != cudaSuccess) {                                                               \
+#define CK(x)                                                                                 \
+  do {                                                                                        \
+    cudaError_t e_ = (x);                                                                     \
+    if (e_ != cudaSuccess) {                                                                  \
       printf("CUDA error %s at %s:%d: %s\n", #x, __FILE__, __LINE__, cudaGetErrorString(e_)); \
-      exit(2);                                                                             \
-    }                                                                                      \
+      exit(2);                                                                                \
+    }                                                                                         \
   } while (0)
 
 template <typename T>
@@ -43,7 +42,7 @@ struct Problem {
   std::vector<float> node_emb;       // [n_nodes+1][256]
   std::vector<int> idx0, idx1, tile_type;
   std::vector<float> W;              // [groups][512][512]
-  std::vector<float> S, tb;          // [rows][512], [groups][512]
+  std::vector<float> S, tb;          // [rows][512] (row-major here; blocked for the device), [groups][512]
   std::vector<float> Wd1, bd1, Wd2, bd2;   // [128][256], [128], [P][128], [P]
 };
 
@@ -52,7 +51,7 @@ static Problem make_problem(int n_nodes, int m_tiles, int groups, unsigned seed)
   p.n_nodes = n_nodes; p.m_tiles = m_tiles; p.groups = groups; p.P = 4;
   std::mt19937 rng(seed);
   std::uniform_real_distribution<float> u(-1.f, 1.f);
-  const int rows = m_tiles * 256;
+  const int rows = m_tiles * 128;
   p.node_emb.resize((size_t)(n_nodes + 1) * 256);
   for (auto &v : p.node_emb) v = u(rng);
   for (int k = 0; k < 256; ++k) p.node_emb[(size_t)n_nodes * 256 + k] = 0.f;
@@ -73,99 +72,118 @@ static Problem make_problem(int n_nodes, int m_tiles, int groups, unsigned seed)
   return p;
 }
 
-template <class C>
-static std::vector<uint8_t> pack_l1(const Problem &p) {
-  const size_t per = (size_t)2 * (512 / C::KC) * C::B_STAGE;
-  std::vector<uint8_t> blob(per * p.groups);
-  for (int g = 0; g < p.groups; ++g) pack_b_blob<C>(&p.W[(size_t)g * 512 * 512], 512, 0, 512, 512, blob.data() + g * per);
-  return blob;
+// host mirror of the node kernel's split pose-embedding rows
+template <class M>
+static std::vector<uint8_t> split_rows(const std::vector<float> &emb) {
+  const size_t rows = emb.size() / 256;
+  std::vector<uint8_t> out(rows * M::PE_ROW_BYTES);
+  for (size_t r = 0; r < rows; ++r)
+    for (int k = 0; k < 256; ++k) {
+      const float x = emb[r * 256 + k];
+      uint8_t *row = out.data() + r * M::PE_ROW_BYTES;
+      if (M::KIND == KIND_TF32) {
+        uint32_t hi = host_tf32_rna(x);
+        float hf; memcpy(&hf, &hi, 4);
+        uint32_t lo = host_tf32_rna(x - hf);
+        memcpy(row + k * 4, &hi, 4); memcpy(row + M::PE_LO_OFF + k * 4, &lo, 4);
+      } else {
+        uint16_t hi = host_bf16_rn(x), lo = host_bf16_rn(x - host_bf16_to_f(hi));
+        memcpy(row + k * 2, &hi, 2); memcpy(row + M::PE_LO_OFF + k * 2, &lo, 2);
+      }
+    }
+  return out;
+}
+
+// unpack operand-format H back to row-major floats [rows][512] (hi + lo)
+template <class M>
+static std::vector<float> unpack_H(const std::vector<uint8_t> &Hop, int m_tiles) {
+  std::vector<float> H((size_t)m_tiles * 128 * 512);
+  const int EPC = 16 / M::ELT;
+  for (int tile = 0; tile < m_tiles * 2; ++tile)
+    for (int kc = 0; kc < M::NKC2; ++kc)
+      for (int r = 0; r < 128; ++r)
+        for (int kk = 0; kk < M::KC; ++kk) {
+          const uint8_t *st = Hop.data() + (size_t)tile * M::H_TILE_BYTES + (size_t)kc * M::A_STAGE;
+          const uint32_t off = sw64_off(r, kk / EPC) + (kk % EPC) * M::ELT;
+          float v = 0.f;
+          for (int part = 0; part < M::NS; ++part) {
+            if (M::KIND == KIND_TF32) { float f; memcpy(&f, st + part * PART + off, 4); v += f; }
+            else { uint16_t h; memcpy(&h, st + part * PART + off, 2); v += host_bf16_to_f(h); }
+          }
+          H[((size_t)(tile >> 1) * 128 + r) * 512 + (tile & 1) * 256 + kc * M::KC + kk] = v;
+        }
+  return H;
 }
 
 struct Report { double max_err, max_ref, ms; };
 
-template <class C>
-static Report run_l1(const Problem &p, const std::vector<double> *ref, int iters, int num_sms, int dbg = 0) {
-  const int rows = p.m_tiles * 256;
-  float *d_emb = dev(p.node_emb), *d_S = dev(p.S), *d_tb = dev(p.tb), *d_H;
-  int *d_i0 = dev(p.idx0), *d_i1 = dev(p.idx1), *d_tt = dev(p.tile_type);
-  std::vector<uint8_t> blob = pack_l1<C>(p);
-  uint8_t *d_blob = dev(blob);
-  CK(cudaMalloc(&d_H, (size_t)rows * 512 * sizeof(float)));
-  CK(cudaMemset(d_H, 0xFF, (size_t)rows * 512 * sizeof(float)));
-  GemmArgs a;
-  memset(&a, 0, sizeof(a));
-  a.a_src[0] = d_emb; a.a_src[1] = d_emb; a.a_idx[0] = d_i0; a.a_idx[1] = d_i1; a.nseg = 2;
-  a.b_blob = d_blob; a.tile_type = d_tt; a.num_m_tiles = p.m_tiles; a.n_tiles = 512 / C::NTILE;
-  a.S = d_S; a.tb = d_tb; a.H = d_H; a.dbg = dbg;
-  CK(launch_gemm_tc<C>(a, num_sms, 0));
-  CK(cudaDeviceSynchronize());
-  Report rep{0, 0, 0};
-  if (ref) {
-    std::vector<float> H((size_t)rows * 512);
-    CK(cudaMemcpy(H.data(), d_H, H.size() * sizeof(float), cudaMemcpyDeviceToHost));
-    int shown = 0;
-    for (size_t i = 0; i < H.size(); ++i) {
-      double e = fabs((double)H[i] - (*ref)[i]);
-      if (!(e == e)) e = 1e30;
-      if (e > rep.max_err) rep.max_err = e;
-      if (fabs((*ref)[i]) > rep.max_ref) rep.max_ref = fabs((*ref)[i]);
-      if (e > 0.05 && shown < 6) { printf("    mismatch row %zu col %zu: got %g want %g\n", i / 512, i % 512, H[i], (*ref)[i]); ++shown; }
-    }
+static void compare(const float *got, const std::vector<double> &ref, Report &rep, const char *what) {
+  int shown = 0;
+  for (size_t i = 0; i < ref.size(); ++i) {
+    double e = fabs((double)got[i] - ref[i]);
+    if (!(e == e)) e = 1e30;
+    if (e > rep.max_err) rep.max_err = e;
+    if (fabs(ref[i]) > rep.max_ref) rep.max_ref = fabs(ref[i]);
+    if (e > 0.05 && shown < 4) { printf("    %s mismatch at %zu: got %g want %g\n", what, i, got[i], ref[i]); ++shown; }
   }
-  if (iters > 0) {
-    cudaEvent_t e0, e1;
-    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-    CK(cudaEventRecord(e0));
-    for (int i = 0; i < iters; ++i) CK(launch_gemm_tc<C>(a, num_sms, 0));
-    CK(cudaEventRecord(e1));
-    CK(cudaEventSynchronize(e1));
-    float ms;
-    CK(cudaEventElapsedTime(&ms, e0, e1));
-    rep.ms = ms / iters;
-  }
-  cudaFree(d_emb); cudaFree(d_S); cudaFree(d_tb); cudaFree(d_H); cudaFree(d_i0); cudaFree(d_i1); cudaFree(d_tt); cudaFree(d_blob);
-  return rep;
 }
 
-template <class C>
-static Report run_dec(const Problem &p, const std::vector<float> &Hin, const std::vector<double> *ref, int iters, int num_sms) {
-  const int rows = (int)(Hin.size() / 256);      // 2 * edge rows
-  float *d_H = dev(Hin), *d_bd1 = dev(p.bd1), *d_w2 = dev(p.Wd2), *d_bd2 = dev(p.bd2), *d_o;
-  std::vector<uint8_t> blob((size_t)(256 / C::KC) * C::B_STAGE);
-  pack_b_blob<C>(p.Wd1.data(), 256, 0, 256, 128, blob.data());
-  uint8_t *d_blob = dev(blob);
-  CK(cudaMalloc(&d_o, (size_t)rows * p.P * sizeof(float)));
-  CK(cudaMemset(d_o, 0xFF, (size_t)rows * p.P * sizeof(float)));
-  GemmArgs a;
+// runs L1 then DEC; returns errors of H (vs ref) in `h` and of o in `o`
+template <class M>
+static void run_chain(const Problem &p, const std::vector<double> *Href, const std::vector<double> *oref, int iters, int sms,
+                      Report &h, Report &o, int dbg = 0) {
+  const int rows = p.m_tiles * 128;
+  std::vector<float> Sblk((size_t)rows * 512);
+  for (int r = 0; r < rows; ++r)
+    for (int c = 0; c < 512; ++c) Sblk[blk_off(r, c)] = p.S[(size_t)r * 512 + c];
+  std::vector<uint8_t> pe = split_rows<M>(p.node_emb);
+  const size_t per = (size_t)2 * M::NKC1 * L1Cfg<M>::B_STAGE;
+  std::vector<uint8_t> b1(per * p.groups), b2((size_t)M::NKC2 * DecCfg<M>::B_STAGE);
+  for (int g = 0; g < p.groups; ++g) pack_b_blob<M, 256>(&p.W[(size_t)g * 512 * 512], 512, 0, 512, 512, b1.data() + g * per);
+  pack_b_blob<M, 128>(p.Wd1.data(), 256, 0, 256, 128, b2.data());
+  uint8_t *d_pe = dev(pe), *d_b1 = dev(b1), *d_b2 = dev(b2), *d_H;
+  float *d_S = dev(Sblk), *d_tb = dev(p.tb), *d_bd1 = dev(p.bd1), *d_w2 = dev(p.Wd2), *d_bd2 = dev(p.bd2), *d_o;
+  int *d_i0 = dev(p.idx0), *d_i1 = dev(p.idx1), *d_tt = dev(p.tile_type);
+  const size_t Hbytes = (size_t)p.m_tiles * 2 * M::H_TILE_BYTES;
+  CK(cudaMalloc(&d_H, Hbytes));
+  CK(cudaMemset(d_H, 0xFF, Hbytes));
+  CK(cudaMalloc(&d_o, (size_t)rows * 2 * p.P * sizeof(float)));
+  CK(cudaMemset(d_o, 0xFF, (size_t)rows * 2 * p.P * sizeof(float)));
+  L1Args a;
   memset(&a, 0, sizeof(a));
-  a.a_src[0] = d_H; a.nseg = 1; a.b_blob = d_blob; a.num_m_tiles = rows / 256; a.n_tiles = 1;
-  a.bd1 = d_bd1; a.Wd2 = d_w2; a.bd2 = d_bd2; a.P = p.P; a.o = d_o;
-  CK(launch_gemm_tc<C>(a, num_sms, 0));
+  a.pe_split = d_pe; a.src_i = d_i0; a.src_j = d_i1; a.b_blob = d_b1; a.tile_type = d_tt; a.num_m_tiles = p.m_tiles;
+  a.S = d_S; a.tb = d_tb; a.H = d_H; a.dbg = dbg;
+  DecArgs d;
+  memset(&d, 0, sizeof(d));
+  d.H = d_H; d.b_blob = d_b2; d.num_tiles = p.m_tiles * 2; d.bd1 = d_bd1; d.Wd2 = d_w2; d.bd2 = d_bd2; d.P = p.P; d.o = d_o; d.dbg = dbg;
+  CK(launch_l1_tc<M>(a, sms, 0));
+  CK(launch_dec_tc<M>(d, sms, 0));
   CK(cudaDeviceSynchronize());
-  Report rep{0, 0, 0};
-  if (ref) {
-    std::vector<float> o((size_t)rows * p.P);
-    CK(cudaMemcpy(o.data(), d_o, o.size() * sizeof(float), cudaMemcpyDeviceToHost));
-    for (size_t i = 0; i < o.size(); ++i) {
-      double e = fabs((double)o[i] - (*ref)[i]);
-      if (!(e == e)) e = 1e30;
-      if (e > rep.max_err) rep.max_err = e;
-      if (fabs((*ref)[i]) > rep.max_ref) rep.max_ref = fabs((*ref)[i]);
-    }
+  h = Report{0, 0, 0}; o = Report{0, 0, 0};
+  if (Href) {
+    std::vector<uint8_t> Hop(Hbytes);
+    CK(cudaMemcpy(Hop.data(), d_H, Hbytes, cudaMemcpyDeviceToHost));
+    std::vector<float> H = unpack_H<M>(Hop, p.m_tiles);
+    compare(H.data(), *Href, h, "H");
+    std::vector<float> oo((size_t)rows * 2 * p.P);
+    CK(cudaMemcpy(oo.data(), d_o, oo.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    compare(oo.data(), *oref, o, "o");
   }
   if (iters > 0) {
-    cudaEvent_t e0, e1;
-    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    cudaEvent_t e0, e1, e2;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1)); CK(cudaEventCreate(&e2));
     CK(cudaEventRecord(e0));
-    for (int i = 0; i < iters; ++i) CK(launch_gemm_tc<C>(a, num_sms, 0));
+    for (int i = 0; i < iters; ++i) CK(launch_l1_tc<M>(a, sms, 0));
     CK(cudaEventRecord(e1));
-    CK(cudaEventSynchronize(e1));
+    for (int i = 0; i < iters; ++i) CK(launch_dec_tc<M>(d, sms, 0));
+    CK(cudaEventRecord(e2));
+    CK(cudaEventSynchronize(e2));
     float ms;
-    CK(cudaEventElapsedTime(&ms, e0, e1));
-    rep.ms = ms / iters;
+    CK(cudaEventElapsedTime(&ms, e0, e1)); h.ms = ms / iters;
+    CK(cudaEventElapsedTime(&ms, e1, e2)); o.ms = ms / iters;
   }
-  cudaFree(d_H); cudaFree(d_bd1); cudaFree(d_w2); cudaFree(d_bd2); cudaFree(d_o); cudaFree(d_blob);
-  return rep;
+  cudaFree(d_pe); cudaFree(d_b1); cudaFree(d_b2); cudaFree(d_H); cudaFree(d_S); cudaFree(d_tb); cudaFree(d_bd1);
+  cudaFree(d_w2); cudaFree(d_bd2); cudaFree(d_o); cudaFree(d_i0); cudaFree(d_i1); cudaFree(d_tt);
 }
 
 int main(int argc, char **argv) {
@@ -176,78 +194,68 @@ int main(int argc, char **argv) {
   printf("device %s, %d SMs, smem/block optin %zu\n", prop.name, sms, prop.sharedMemPerBlockOptin);
   int fails = 0;
   {
-    // ---- numerics: 11 tiles of 256 rows, 3 weight groups ---------------------------------------------
-    Problem p = make_problem(1000, 11, 3, 1);
-    const int rows = p.m_tiles * 256;
-    std::vector<double> ref((size_t)rows * 512);
-    std::vector<float> Href((size_t)rows * 512);
+    // ---- numerics: 21 tiles of 128 edges (ragged vs the grid on purpose), 3 weight groups ---------------
+    Problem p = make_problem(1000, 21, 3, 1);
+    const int rows = p.m_tiles * 128;
+    std::vector<double> Href((size_t)rows * 512), oref((size_t)rows * 2 * p.P);
     for (int r = 0; r < rows; ++r) {
       const float *a0 = &p.node_emb[(size_t)p.idx0[r] * 256], *a1 = &p.node_emb[(size_t)p.idx1[r] * 256];
-      const int g = p.tile_type[r / 256];
+      const int g = p.tile_type[r / 128];
       for (int n = 0; n < 512; ++n) {
         const float *w = &p.W[((size_t)g * 512 + n) * 512];
         double acc = 0;
         for (int k = 0; k < 256; ++k) acc += (double)a0[k] * w[k] + (double)a1[k] * w[256 + k];
-        double v = silu_d(acc + p.S[(size_t)r * 512 + n] + p.tb[g * 512 + n]);
-        ref[(size_t)r * 512 + n] = v;
-        Href[(size_t)r * 512 + n] = (float)v;
+        Href[(size_t)r * 512 + n] = silu_d(acc + p.S[(size_t)r * 512 + n] + p.tb[g * 512 + n]);
       }
-    }
-    std::vector<double> oref((size_t)rows * 2 * p.P);
-    for (int q = 0; q < rows * 2; ++q) {
-      double d[128];
-      for (int j = 0; j < 128; ++j) {
-        double acc = 0;
-        for (int k = 0; k < 256; ++k) acc += (double)Href[(size_t)q * 256 + k] * p.Wd1[j * 256 + k];
-        d[j] = silu_d(acc + p.bd1[j]);
-      }
-      for (int pp = 0; pp < p.P; ++pp) {
-        double acc = 0;
-        for (int j = 0; j < 128; ++j) acc += d[j] * p.Wd2[pp * 128 + j];
-        oref[(size_t)q * p.P + pp] = acc + p.bd2[pp];
+      for (int slot = 0; slot < 2; ++slot) {
+        double dd[128];
+        for (int j = 0; j < 128; ++j) {
+          double acc = 0;
+          for (int k = 0; k < 256; ++k) acc += Href[(size_t)r * 512 + slot * 256 + k] * p.Wd1[j * 256 + k];
+          dd[j] = silu_d(acc + p.bd1[j]);
+        }
+        for (int pp = 0; pp < p.P; ++pp) {
+          double acc = 0;
+          for (int j = 0; j < 128; ++j) acc += dd[j] * p.Wd2[pp * 128 + j];
+          oref[((size_t)r * 2 + slot) * p.P + pp] = acc + p.bd2[pp];
+        }
       }
     }
     auto chk = [&](const char *name, Report r, double tol) {
       bool ok = r.max_err <= tol * (r.max_ref > 1 ? r.max_ref : 1);
-      printf("%-22s max_err %.3e (max|ref| %.3f) tol %.1e  %s\n", name, r.max_err, r.max_ref, tol, ok ? "PASS" : "FAIL");
+      printf("%-14s max_err %.3e (max|ref| %.3f) tol %.1e  %s\n", name, r.max_err, r.max_ref, tol, ok ? "PASS" : "FAIL");
       if (!ok) ++fails;
     };
-    chk("l1  tf32x3", run_l1<Cfg<KIND_TF32, 3, 256, EPI_TC_L1>>(p, &ref, 0, sms), 3e-6);
-    chk("l1  bf16x3", run_l1<Cfg<KIND_BF16, 3, 256, EPI_TC_L1>>(p, &ref, 0, sms), 1e-4);
-    chk("l1  tf32", run_l1<Cfg<KIND_TF32, 1, 256, EPI_TC_L1>>(p, &ref, 0, sms), 5e-3);
-    chk("l1  bf16", run_l1<Cfg<KIND_BF16, 1, 256, EPI_TC_L1>>(p, &ref, 0, sms), 4e-2);
-    chk("dec tf32x3", run_dec<Cfg<KIND_TF32, 3, 128, EPI_TC_DEC>>(p, Href, &oref, 0, sms), 3e-6);
-    chk("dec bf16x3", run_dec<Cfg<KIND_BF16, 3, 128, EPI_TC_DEC>>(p, Href, &oref, 0, sms), 1e-4);
-    chk("dec tf32", run_dec<Cfg<KIND_TF32, 1, 128, EPI_TC_DEC>>(p, Href, &oref, 0, sms), 5e-3);
-    chk("dec bf16", run_dec<Cfg<KIND_BF16, 1, 128, EPI_TC_DEC>>(p, Href, &oref, 0, sms), 4e-2);
+    Report h, o;
+    run_chain<Mode<KIND_TF32, 3>>(p, &Href, &oref, 0, sms, h, o); chk("H tf32x3", h, 3e-6); chk("o tf32x3", o, 3e-6);
+    run_chain<Mode<KIND_BF16, 3>>(p, &Href, &oref, 0, sms, h, o); chk("H bf16x3", h, 2e-5); chk("o bf16x3", o, 2e-5);
+    run_chain<Mode<KIND_TF32, 1>>(p, &Href, &oref, 0, sms, h, o); chk("H tf32", h, 5e-3); chk("o tf32", o, 5e-3);
+    run_chain<Mode<KIND_BF16, 1>>(p, &Href, &oref, 0, sms, h, o); chk("H bf16", h, 4e-2); chk("o bf16", o, 4e-2);
   }
   if (perf && fails == 0) {
-    // ---- throughput at the config-2 size: 317 edge tiles (81 152 rows), 13 weight groups ---------------
-    Problem p = make_problem(9216, 317, 13, 2);
-    const double fl1 = 2.0 * 317 * 256 * 512 * 512, fdec = 2.0 * 317 * 512 * 128 * 256;
-    std::vector<float> Hin((size_t)317 * 256 * 512);
-    for (size_t i = 0; i < Hin.size(); ++i) Hin[i] = (float)((i * 2654435761u) % 1000) / 1000.f - 0.5f;
-    auto pr = [&](const char *name, Report r, double fl) { printf("%-34s %.3f ms  %.1f TFLOP/s (algorithmic)\n", name, r.ms, fl / r.ms / 1e9); };
-    pr("l1  tf32x3", run_l1<Cfg<KIND_TF32, 3, 256, EPI_TC_L1>>(p, nullptr, 20, sms), fl1);
-    pr("l1  bf16x3", run_l1<Cfg<KIND_BF16, 3, 256, EPI_TC_L1>>(p, nullptr, 20, sms), fl1);
-    pr("l1  tf32", run_l1<Cfg<KIND_TF32, 1, 256, EPI_TC_L1>>(p, nullptr, 20, sms), fl1);
-    pr("l1  bf16", run_l1<Cfg<KIND_BF16, 1, 256, EPI_TC_L1>>(p, nullptr, 20, sms), fl1);
-    const char *abl[] = {"none", "noA", "noB", "noA,noB", "noEpiIO", "noA,noEpiIO", "noB,noEpiIO", "MMA+sync only",
-                         "noMMA", "noMMA,noA", "noMMA,noB", "noMMA,noA,noB", "noMMA,noEpiIO", "", "", "sync skeleton"};
-    for (int dbg : {1, 2, 3, 4, 7, 8, 9, 10, 12, 15}) {
+    // ---- throughput at the config-2 size: 633 edge tiles (81 024 rows), 13 weight groups ---------------
+    Problem p = make_problem(9216, 633, 13, 2);
+    const double fl1 = 2.0 * 633 * 128 * 512 * 512, fdec = 2.0 * 633 * 256 * 128 * 256;
+    auto pr = [&](const char *name, Report h, Report o) {
+      printf("%-30s l1 %.3f ms %6.1f TFLOP/s | dec %.3f ms %6.1f TFLOP/s\n", name, h.ms, fl1 / h.ms / 1e9, o.ms, fdec / o.ms / 1e9);
+    };
+    Report h, o;
+    run_chain<Mode<KIND_TF32, 3>>(p, nullptr, nullptr, 20, sms, h, o); pr("tf32x3", h, o);
+    run_chain<Mode<KIND_BF16, 3>>(p, nullptr, nullptr, 20, sms, h, o); pr("bf16x3", h, o);
+    run_chain<Mode<KIND_TF32, 1>>(p, nullptr, nullptr, 20, sms, h, o); pr("tf32", h, o);
+    run_chain<Mode<KIND_BF16, 1>>(p, nullptr, nullptr, 20, sms, h, o); pr("bf16", h, o);
+    const char *abl[16] = {"none", "noA", "noB", "noA,noB", "noEpiIO", "noA,noEpiIO", "noB,noEpiIO", "MMA+sync only",
+                           "noMMA", "noMMA,noA", "noMMA,noB", "noMMA,noA,noB", "noMMA,noEpiIO", "", "", "sync skeleton"};
+    for (int dbg : {1, 2, 4, 7, 8, 15}) {
       char nm[64];
-      snprintf(nm, sizeof nm, "l1 tf32x3 [%s]", abl[dbg]);
-      pr(nm, run_l1<Cfg<KIND_TF32, 3, 256, EPI_TC_L1>>(p, nullptr, 10, sms, dbg), fl1);
+      snprintf(nm, sizeof nm, "tf32x3 [%s]", abl[dbg]);
+      run_chain<Mode<KIND_TF32, 3>>(p, nullptr, nullptr, 10, sms, h, o, dbg); pr(nm, h, o);
     }
-    for (int dbg : {1, 2, 4, 7, 8}) {
+    for (int dbg : {1, 2, 4, 7, 8, 15}) {
       char nm[64];
-      snprintf(nm, sizeof nm, "l1 bf16x3 [%s]", abl[dbg]);
-      pr(nm, run_l1<Cfg<KIND_BF16, 3, 256, EPI_TC_L1>>(p, nullptr, 10, sms, dbg), fl1);
+      snprintf(nm, sizeof nm, "bf16x3 [%s]", abl[dbg]);
+      run_chain<Mode<KIND_BF16, 3>>(p, nullptr, nullptr, 10, sms, h, o, dbg); pr(nm, h, o);
     }
-    pr("dec tf32x3", run_dec<Cfg<KIND_TF32, 3, 128, EPI_TC_DEC>>(p, Hin, nullptr, 20, sms), fdec);
-    pr("dec bf16x3", run_dec<Cfg<KIND_BF16, 3, 128, EPI_TC_DEC>>(p, Hin, nullptr, 20, sms), fdec);
-    pr("dec tf32", run_dec<Cfg<KIND_TF32, 1, 128, EPI_TC_DEC>>(p, Hin, nullptr, 20, sms), fdec);
-    pr("dec bf16", run_dec<Cfg<KIND_BF16, 1, 128, EPI_TC_DEC>>(p, Hin, nullptr, 20, sms), fdec);
   }
   printf(fails ? "RESULT: FAIL (%d)\n" : "RESULT: PASS\n", fails);
   return fails ? 1 : 0;
