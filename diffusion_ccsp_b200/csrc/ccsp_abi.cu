@@ -347,8 +347,13 @@ static NodeArgs node_args_base(CcspPlan *p) {
 }
 
 static int launch_node(CcspPlan *p, const NodeArgs &a, cudaStream_t st) {
-  unsigned blocks = (unsigned)((p->n + 1 + ENC_ROWS - 1) / ENC_ROWS);
-  k_node<<<blocks, 256, 0, st>>>(a);
+  static bool configured = false;
+  if (!configured) {
+    CCSP_CUDA_TRY(cudaFuncSetAttribute(k_node, cudaFuncAttributeMaxDynamicSharedMemorySize, NODE_SMEM_BYTES));
+    configured = true;
+  }
+  unsigned blocks = (unsigned)((p->n + 1 + NODE_ROWS - 1) / NODE_ROWS);
+  k_node<<<blocks, NODE_THREADS, NODE_SMEM_BYTES, st>>>(a);
   CCSP_LAUNCH_CHECK();
   return CCSP_OK;
 }

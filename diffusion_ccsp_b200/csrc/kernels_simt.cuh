@@ -155,13 +155,32 @@ struct NodeArgs {
   void *pe;
 };
 
-__global__ void __launch_bounds__(256) k_node(NodeArgs A) {
-  __shared__ float xs[ENC_ROWS][CCSP_MAXP];
-  __shared__ float h[ENC_ROWS][CCSP_HH];
-  const int tid = threadIdx.x, row0 = blockIdx.x * ENC_ROWS;
+// 64 nodes per block, 512 threads.  Stage 0: one (node, component) pair per thread; stage 1: layer 1 of the
+// pose encoder (P -> 128); stage 2: layer 2 (128 -> 256) as a register-tiled FP32 GEMM (4 rows x 8 columns
+// per thread, W2t streamed through shared memory in 16-row slabs).  The tensor-core modes use the hardware
+// exp2/rcp SiLU (as the edge kernels do); the FP32 validation mode keeps the libm-accurate one.
+#define NODE_ROWS 64
+#define NODE_THREADS 512
+#define NODE_LDH (CCSP_HH + 4)
+constexpr int NODE_SMEM_BYTES = (NODE_ROWS * CCSP_MAXP + NODE_ROWS * NODE_LDH + 2 * 16 * CCSP_H + CCSP_HH * (CCSP_MAXP + 1)) * 4;
+
+__device__ __forceinline__ float silu_sel(float x, bool fast) { return fast ? __fdividef(x, 1.0f + __expf(-x)) : silu_f(x); }
+
+__global__ void __launch_bounds__(NODE_THREADS) k_node(NodeArgs A) {
+  extern __shared__ __align__(16) float node_smem[];
+  float (*xs)[CCSP_MAXP] = reinterpret_cast<float (*)[CCSP_MAXP]>(node_smem);
+  float (*h)[NODE_LDH] = reinterpret_cast<float (*)[NODE_LDH]>(node_smem + NODE_ROWS * CCSP_MAXP);
+  float (*Bs)[16][CCSP_H] = reinterpret_cast<float (*)[16][CCSP_H]>(node_smem + NODE_ROWS * CCSP_MAXP + NODE_ROWS * NODE_LDH);
+  float *w0s = node_smem + NODE_ROWS * CCSP_MAXP + NODE_ROWS * NODE_LDH + 2 * 16 * CCSP_H;   // [128][P] then b0 [128]
+  const int tid = threadIdx.x, row0 = blockIdx.x * NODE_ROWS;
   const int P = A.P;
-  if (tid < ENC_ROWS * CCSP_MAXP) {
-    const int r = tid / CCSP_MAXP, p = tid % CCSP_MAXP, v = row0 + r;
+  const bool fast = A.pe_fmt != 0;
+  if (A.mode != NODE_EPS_OUT) {
+    for (int i = tid; i < CCSP_HH * P; i += NODE_THREADS) w0s[i] = __ldg(&A.W0[i]);
+    for (int i = tid; i < CCSP_HH; i += NODE_THREADS) w0s[CCSP_HH * CCSP_MAXP + i] = __ldg(&A.b0[i]);
+  }
+  for (int slot = tid; slot < NODE_ROWS * CCSP_MAXP; slot += NODE_THREADS) {
+    const int r = slot / CCSP_MAXP, p = slot % CCSP_MAXP, v = row0 + r;
     float xn = 0.f;
     if (v < A.n && p < P) {
       const size_t ix = (size_t)v * P + p;
@@ -185,9 +204,16 @@ __global__ void __launch_bounds__(256) k_node(NodeArgs A) {
           if (masked) {
             eps = A.xtail[ix];
           } else {
+            // same accumulation order as the reference's scatter_add_ (sequential adds); loads batched by 4
             const int k0 = A.node_ptr[v], k1 = A.node_ptr[v + 1];
             float acc = 0.f;
-            for (int k = k0; k < k1; ++k) acc = __fadd_rn(acc, A.o[(size_t)A.node_src[k] * P + p]);
+            int k = k0;
+            for (; k + 4 <= k1; k += 4) {
+              const int s0 = A.node_src[k], s1 = A.node_src[k + 1], s2 = A.node_src[k + 2], s3 = A.node_src[k + 3];
+              const float o0 = A.o[(size_t)s0 * P + p], o1 = A.o[(size_t)s1 * P + p], o2 = A.o[(size_t)s2 * P + p], o3 = A.o[(size_t)s3 * P + p];
+              acc = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(acc, o0), o1), o2), o3);
+            }
+            for (; k < k1; ++k) acc = __fadd_rn(acc, A.o[(size_t)A.node_src[k] * P + p]);
             eps = A.normalize ? acc / sqrtf((float)(k1 - k0)) : acc;
           }
         }
@@ -216,28 +242,90 @@ __global__ void __launch_bounds__(256) k_node(NodeArgs A) {
   }
   if (A.mode == NODE_EPS_OUT) return;
   __syncthreads();
-  float o[ENC_ROWS];
-  encoder_rows_16(xs, P, A.W0, A.b0, A.W2t, A.b2, h, o);
+  // ---- layer 1: 64 x 128 outputs
+  for (int idx = tid; idx < NODE_ROWS * CCSP_HH; idx += NODE_THREADS) {
+    const int r = idx / CCSP_HH, j = idx % CCSP_HH;
+    float acc = 0.f;
+    for (int d = 0; d < P; ++d) acc = fmaf(xs[r][d], w0s[j * P + d], acc);
+    h[r][j] = silu_sel(acc + w0s[CCSP_HH * CCSP_MAXP + j], fast);
+  }
+  // ---- layer 2: out[64 x 256] = h[64 x 128] . W2t[128 x 256]; thread = rows 4 ty.., cols 4 tx.. and 128 + 4 tx..
+  const int tx = tid & 31, ty = tid >> 5;
+  float acc[4][8];
 #pragma unroll
-  for (int r = 0; r < ENC_ROWS; ++r) {
-    const int v = row0 + r;
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  auto load_slab = [&](int slab, int buf) {      // 16 x 256 floats = 1024 float4, 2 per thread
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int f4 = q * NODE_THREADS + tid, kk = f4 >> 6, c4 = f4 & 63;
+      *reinterpret_cast<float4 *>(&Bs[buf][kk][c4 * 4]) = __ldg(reinterpret_cast<const float4 *>(A.W2t + (size_t)(slab * 16 + kk) * CCSP_H + c4 * 4));
+    }
+  };
+  load_slab(0, 0);
+  __syncthreads();
+  for (int slab = 0; slab < CCSP_HH / 16; ++slab) {
+    const int buf = slab & 1;
+    if (slab + 1 < CCSP_HH / 16) load_slab(slab + 1, buf ^ 1);
+#pragma unroll
+    for (int k4 = 0; k4 < 16; k4 += 4) {
+      float4 a4[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a4[i] = *reinterpret_cast<const float4 *>(&h[ty * 4 + i][slab * 16 + k4]);
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        const float4 b0 = *reinterpret_cast<const float4 *>(&Bs[buf][k4 + kk][tx * 4]);
+        const float4 b1 = *reinterpret_cast<const float4 *>(&Bs[buf][k4 + kk][128 + tx * 4]);
+        const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float a = kk == 0 ? a4[i].x : kk == 1 ? a4[i].y : kk == 2 ? a4[i].z : a4[i].w;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a, b[j], acc[i][j]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // ---- epilogue: SiLU, write the pose embedding in the format the edge kernels consume
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int v = row0 + ty * 4 + i;
     if (v > A.n) continue;
-    const float e = v < A.n ? o[r] : 0.f;
-    if (A.pe_fmt == 0) {
-      reinterpret_cast<float *>(A.pe)[(size_t)v * CCSP_H + tid] = e;
-    } else if (A.pe_fmt == 1) {          // hi = rna_tf32(e), lo = rna_tf32(e - hi)
-      uint32_t hi, lo;
-      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(e));
-      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(e - __uint_as_float(hi)));
-      uint32_t *row = reinterpret_cast<uint32_t *>(A.pe) + (size_t)v * (2 * CCSP_H);
-      row[tid] = hi;
-      row[CCSP_H + tid] = lo;
-    } else {                             // hi = rn_bf16(e), lo = rn_bf16(e - hi)
-      const __nv_bfloat16 hi = __float2bfloat16_rn(e);
-      const __nv_bfloat16 lo = __float2bfloat16_rn(e - __bfloat162float(hi));
-      __nv_bfloat16 *row = reinterpret_cast<__nv_bfloat16 *>(A.pe) + (size_t)v * (2 * CCSP_H);
-      row[tid] = hi;
-      row[CCSP_H + tid] = lo;
+#pragma unroll
+    for (int hb = 0; hb < 2; ++hb) {
+      const int col = hb * 128 + tx * 4;
+      const float4 bb = __ldg(reinterpret_cast<const float4 *>(A.b2 + col));
+      float e[4] = {silu_sel(acc[i][hb * 4 + 0] + bb.x, fast), silu_sel(acc[i][hb * 4 + 1] + bb.y, fast),
+                    silu_sel(acc[i][hb * 4 + 2] + bb.z, fast), silu_sel(acc[i][hb * 4 + 3] + bb.w, fast)};
+      if (v == A.n) e[0] = e[1] = e[2] = e[3] = 0.f;           // zero row read by padded edges
+      if (A.pe_fmt == 0) {
+        *reinterpret_cast<float4 *>(reinterpret_cast<float *>(A.pe) + (size_t)v * CCSP_H + col) = make_float4(e[0], e[1], e[2], e[3]);
+      } else if (A.pe_fmt == 1) {        // hi = rna_tf32(e), lo = rna_tf32(e - hi)
+        uint4 hi, lo;
+        uint32_t *hp = &hi.x, *lp = &lo.x;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hp[c]) : "f"(e[c]));
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lp[c]) : "f"(e[c] - __uint_as_float(hp[c])));
+        }
+        uint32_t *row = reinterpret_cast<uint32_t *>(A.pe) + (size_t)v * (2 * CCSP_H);
+        *reinterpret_cast<uint4 *>(row + col) = hi;
+        *reinterpret_cast<uint4 *>(row + CCSP_H + col) = lo;
+      } else {                           // hi = rn_bf16(e), lo = rn_bf16(e - hi)
+        float g[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) g[c] = __bfloat162float(__float2bfloat16_rn(e[c]));
+        __nv_bfloat162 h01 = __floats2bfloat162_rn(g[0], g[1]), h23 = __floats2bfloat162_rn(g[2], g[3]);
+        __nv_bfloat162 l01 = __floats2bfloat162_rn(e[0] - g[0], e[1] - g[1]), l23 = __floats2bfloat162_rn(e[2] - g[2], e[3] - g[3]);
+        __nv_bfloat16 *row = reinterpret_cast<__nv_bfloat16 *>(A.pe) + (size_t)v * (2 * CCSP_H);
+        uint2 hv, lv;
+        hv.x = *reinterpret_cast<uint32_t *>(&h01); hv.y = *reinterpret_cast<uint32_t *>(&h23);
+        lv.x = *reinterpret_cast<uint32_t *>(&l01); lv.y = *reinterpret_cast<uint32_t *>(&l23);
+        *reinterpret_cast<uint2 *>(row + col) = hv;
+        *reinterpret_cast<uint2 *>(row + CCSP_H + col) = lv;
+      }
     }
   }
 }

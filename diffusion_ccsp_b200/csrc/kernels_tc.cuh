@@ -390,8 +390,9 @@ __global__ void __launch_bounds__(L1Cfg<M>::THREADS, 1) k_edge_l1_tc(const L1Arg
       float4 sn[8];                                                    // prefetched one 32-column chunk ahead
 #pragma unroll
       for (int j = 0; j < 8; ++j) sn[j] = (A.dbg & 4) ? make_float4(0.f, 0.f, 0.f, 0.f) : ldg_nc_f4(Sblk + j * 32);
+      const float tb_mine = __ldg(&A.tb[(size_t)grp * CCSP_H2 + slot * 256 + threadIdx.x]);
       asm volatile("bar.sync 1, 256;" ::: "memory");                  // previous tile's readers of tb_s are done
-      tb_s[threadIdx.x] = __ldg(&A.tb[(size_t)grp * CCSP_H2 + slot * 256 + threadIdx.x]);
+      tb_s[threadIdx.x] = tb_mine;
       asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(&tfull_bar[buf], (tcount / C::NBUF) & 1);
       tc_fence_after();
