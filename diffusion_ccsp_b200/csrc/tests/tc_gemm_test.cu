@@ -186,6 +186,49 @@ static void run_chain(const Problem &p, const std::vector<double> *Href, const s
   cudaFree(d_w2); cudaFree(d_bd2); cudaFree(d_o); cudaFree(d_i0); cudaFree(d_i1); cudaFree(d_tt);
 }
 
+// fused kernel: o only
+template <class M>
+static void run_fused(const Problem &p, const std::vector<double> *oref, int iters, int sms, Report &o, int dbg = 0) {
+  const int rows = p.m_tiles * 128;
+  std::vector<float> Sblk((size_t)rows * 512);
+  for (int r = 0; r < rows; ++r)
+    for (int c = 0; c < 512; ++c) Sblk[blk_off(r, c)] = p.S[(size_t)r * 512 + c];
+  std::vector<uint8_t> pe = split_rows<M>(p.node_emb);
+  const size_t per = (size_t)2 * M::NKC1 * FusedCfg<M>::B1_STAGE;
+  std::vector<uint8_t> b1(per * p.groups), b2((size_t)M::NKC2 * FusedCfg<M>::B2_STAGE);
+  for (int g = 0; g < p.groups; ++g) pack_b_blob<M, 256>(&p.W[(size_t)g * 512 * 512], 512, 0, 512, 512, b1.data() + g * per);
+  pack_b_blob<M, 128>(p.Wd1.data(), 256, 0, 256, 128, b2.data());
+  uint8_t *d_pe = dev(pe), *d_b1 = dev(b1), *d_b2 = dev(b2);
+  float *d_S = dev(Sblk), *d_tb = dev(p.tb), *d_bd1 = dev(p.bd1), *d_w2 = dev(p.Wd2), *d_bd2 = dev(p.bd2), *d_o;
+  int *d_i0 = dev(p.idx0), *d_i1 = dev(p.idx1), *d_tt = dev(p.tile_type);
+  CK(cudaMalloc(&d_o, (size_t)rows * 2 * p.P * sizeof(float)));
+  CK(cudaMemset(d_o, 0xFF, (size_t)rows * 2 * p.P * sizeof(float)));
+  FusedArgs a;
+  memset(&a, 0, sizeof(a));
+  a.pe_split = d_pe; a.src_i = d_i0; a.src_j = d_i1; a.b_blob = d_b1; a.w_blob = d_b2; a.tile_type = d_tt; a.num_m_tiles = p.m_tiles;
+  a.S = d_S; a.tb = d_tb; a.bd1 = d_bd1; a.Wd2 = d_w2; a.bd2 = d_bd2; a.P = p.P; a.o = d_o; a.dbg = dbg;
+  CK(launch_fused_tc<M>(a, sms, 0));
+  CK(cudaDeviceSynchronize());
+  o = Report{0, 0, 0};
+  if (oref) {
+    std::vector<float> oo((size_t)rows * 2 * p.P);
+    CK(cudaMemcpy(oo.data(), d_o, oo.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    compare(oo.data(), *oref, o, "o(fused)");
+  }
+  if (iters > 0) {
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    CK(cudaEventRecord(e0));
+    for (int i = 0; i < iters; ++i) CK(launch_fused_tc<M>(a, sms, 0));
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    float ms;
+    CK(cudaEventElapsedTime(&ms, e0, e1)); o.ms = ms / iters;
+  }
+  cudaFree(d_pe); cudaFree(d_b1); cudaFree(d_b2); cudaFree(d_S); cudaFree(d_tb); cudaFree(d_bd1);
+  cudaFree(d_w2); cudaFree(d_bd2); cudaFree(d_o); cudaFree(d_i0); cudaFree(d_i1); cudaFree(d_tt);
+}
+
 int main(int argc, char **argv) {
   const bool perf = argc > 1 && !strcmp(argv[1], "perf");
   cudaDeviceProp prop;
@@ -231,6 +274,8 @@ int main(int argc, char **argv) {
     run_chain<Mode<KIND_BF16, 3>>(p, &Href, &oref, 0, sms, h, o); chk("H bf16x3", h, 2e-5); chk("o bf16x3", o, 2e-5);
     run_chain<Mode<KIND_TF32, 1>>(p, &Href, &oref, 0, sms, h, o); chk("H tf32", h, 5e-3); chk("o tf32", o, 5e-3);
     run_chain<Mode<KIND_BF16, 1>>(p, &Href, &oref, 0, sms, h, o); chk("H bf16", h, 4e-2); chk("o bf16", o, 4e-2);
+    run_fused<Mode<KIND_BF16, 3>>(p, &oref, 0, sms, o); chk("o fused bf16x3", o, 2e-5);
+    run_fused<Mode<KIND_BF16, 1>>(p, &oref, 0, sms, o); chk("o fused bf16", o, 4e-2);
   }
   if (perf && fails == 0) {
     // ---- throughput at the config-2 size: 633 edge tiles (81 024 rows), 13 weight groups ---------------
@@ -244,6 +289,16 @@ int main(int argc, char **argv) {
     run_chain<Mode<KIND_BF16, 3>>(p, nullptr, nullptr, 20, sms, h, o); pr("bf16x3", h, o);
     run_chain<Mode<KIND_TF32, 1>>(p, nullptr, nullptr, 20, sms, h, o); pr("tf32", h, o);
     run_chain<Mode<KIND_BF16, 1>>(p, nullptr, nullptr, 20, sms, h, o); pr("bf16", h, o);
+    {
+      Report f;
+      const double ff = fl1 + fdec;
+      run_fused<Mode<KIND_BF16, 3>>(p, nullptr, 20, sms, f); printf("%-30s fused %.3f ms %6.1f TFLOP/s\n", "bf16x3 fused", f.ms, ff / f.ms / 1e9);
+      run_fused<Mode<KIND_BF16, 1>>(p, nullptr, 20, sms, f); printf("%-30s fused %.3f ms %6.1f TFLOP/s\n", "bf16 fused", f.ms, ff / f.ms / 1e9);
+      for (int dbg : {1, 2, 4, 7, 8, 15}) {
+        run_fused<Mode<KIND_BF16, 3>>(p, nullptr, 10, sms, f, dbg);
+        printf("bf16x3 fused dbg=%-2d              fused %.3f ms %6.1f TFLOP/s\n", dbg, f.ms, ff / f.ms / 1e9);
+      }
+    }
     const char *abl[16] = {"none", "noA", "noB", "noA,noB", "noEpiIO", "noA,noEpiIO", "noB,noEpiIO", "MMA+sync only",
                            "noMMA", "noMMA,noA", "noMMA,noB", "noMMA,noA,noB", "noMMA,noEpiIO", "", "", "sync skeleton"};
     for (int dbg : {1, 2, 4, 7, 8, 15}) {
