@@ -148,7 +148,7 @@ def run_reference(args):
         return
     from diffusion_ccsp_b200 import scenes, synthetic
     mode, dims = 'qualitative', synthetic.DIMS['qualitative']
-    sd = synthetic.make_state_dict(dims, mode, seed=0)
+    sd = synthetic.make_trained_state_dict()
     batch = scenes.qualitative_batch(args.batch, WORKLOAD['n_obj'])
     T, K = args.timesteps, WORKLOAD['K']
     import oracle.ccsp_oracle  # noqa: F401  (warm numpy/BLAS)
@@ -201,7 +201,7 @@ def run_ours(args):
     math = args.math or default_math()
     mode, dims = 'qualitative', synthetic.DIMS['qualitative']
     P = dims[-1][0]
-    sd = synthetic.make_state_dict(dims, mode, seed=0)
+    sd = synthetic.make_trained_state_dict()          # realistic O(1) regime (tests/golden/make_trained_fixture.py)
     T, K, B = args.timesteps, WORKLOAD['K'], args.batch
     batch = scenes.qualitative_batch(B, WORKLOAD['n_obj'], seed=rank)       # every rank its own scenes
     den = ConstraintDiffuser(dims=dims, input_mode=mode, device=dev, verbose=False, math=math)
@@ -251,7 +251,9 @@ def run_ours(args):
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    assert bool(torch.isfinite(out[~batch.mask.bool().to(dev)]).any()) or True
+    free = out[~batch.mask.bool().to(dev)]
+    result_stats = dict(finite_frac=float(torch.isfinite(free).float().mean()), max_abs=float(free.abs().max()),
+                        frac_in_unit_box=float((free.abs() <= 1.05).float().mean()))
     value = world * B / (ms / 1e3)
 
     # ---- e2e: public API with HOST buffers: plan build (H2D) + sample + D2H, wall clock ------------
@@ -300,9 +302,9 @@ def run_ours(args):
         line = dict(metric='scenes_per_sec', value=value, unit='scenes/s', n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=ms, higher_is_better=True, scaling='weak', vs_baseline=None, dtype=math, data='synthetic',
                     config=dict(workload=workload_name(args), timesteps=T, ula_steps=K, scenes_per_gpu=B, nodes_per_gpu=n,
-                                edges_per_gpu=E, denoiser_evals_per_step=evals, weights='random-init (seeded), 9.15 M params',
+                                edges_per_gpu=E, denoiser_evals_per_step=evals, weights='seeded init, 74k parameters (pose encoder/decoder, mlps biases) trained offline with the reference loss; 9.15 M params',
                                 noise='in-kernel Philox4x32-10', l2='explicit 256 MiB flush between steps; static term + activations (2 x %d MB) exceed L2' % (plan.edge_rows * 512 * 4 >> 20)),
-                    clocks=clocks, e2e=e2e, gpu_launches=int(launches),
+                    clocks=clocks, e2e=e2e, gpu_launches=int(launches), result=result_stats,
                     roofline=roofline,
                     kernels=dict(avg_ms=dict(edge_l1=l1_ms, edge_dec=dec_ms, node=node_ms),
                                  share_of_step=dict(edge_l1=l1_ms * evals / ms, edge_dec=dec_ms * evals / ms, node=node_ms * evals / ms)),

@@ -231,7 +231,7 @@ static int ensure_time_table(CcspModel *m, int T, cudaStream_t st) {
 // ---- tensor-core modes -----------------------------------------------------------------------------
 template <class M>
 static int pack_tc_blobs(CcspModel *m, int math) {
-  using L1 = tc::L1Cfg<M>;
+  using L1 = tc::L1Cfg<M, 1>;
   using Dec = tc::DecCfg<M>;
   const size_t per = (size_t)2 * M::NKC1 * L1::B_STAGE;
   std::vector<uint8_t> b1(per * m->C);
@@ -285,7 +285,7 @@ static int launch_edge_tc(CcspPlan *p, const float *tb, cudaStream_t st, cudaEve
   a.b_blob = m->blob_l1[m->math]; a.tile_type = p->tile_type;
   a.num_m_tiles = (int)(p->Epad / CCSP_TILE_M);
   a.S = p->S; a.tb = tb; a.H = p->Hop[m->math];
-  CCSP_CUDA_TRY((tc::launch_l1_tc<M>(a, m->num_sms, st)));
+  CCSP_CUDA_TRY((tc::launch_l1_tc<M, CCSP_CLUSTER>(a, m->num_sms, st)));
   count_launch();
   if (mid) CCSP_CUDA_TRY(cudaEventRecord(mid, st));
   tc::DecArgs d;
@@ -435,7 +435,7 @@ int ccsp_plan_create(CcspModel *m, const float *x, int64_t n, int32_t F, const i
   std::vector<int64_t> start(C + 1, 0);
   std::vector<int> tile_type;
   for (int c = 0; c < C; ++c) {
-    int64_t tiles = (cnt[c] + CCSP_TILE_M - 1) / CCSP_TILE_M;
+    int64_t tiles = (cnt[c] + CCSP_PAD_M - 1) / CCSP_PAD_M * CCSP_CLUSTER;   // whole cluster groups of 128-row tiles
     start[c + 1] = start[c] + tiles * CCSP_TILE_M;
     for (int64_t k = 0; k < tiles; ++k) tile_type.push_back(c);
   }

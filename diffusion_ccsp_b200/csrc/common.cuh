@@ -7,7 +7,9 @@
 #define CCSP_H 256            // hidden_dim
 #define CCSP_H2 512           // 2 * hidden_dim (first-layer output width, one half per edge endpoint)
 #define CCSP_HH 128           // hidden_dim / 2
-#define CCSP_TILE_M 128       // edge rows per tile (padded per constraint type)
+#define CCSP_TILE_M 128       // edge rows per tensor-core tile
+#define CCSP_CLUSTER 2        // thread-block-cluster size of the first-layer kernel (weight-stage multicast)
+#define CCSP_PAD_M (CCSP_TILE_M * CCSP_CLUSTER)   // every constraint type is padded to whole cluster groups of tiles
 #define CCSP_MAXP 8
 
 namespace ccsp {

@@ -58,7 +58,7 @@ static Problem make_problem(int n_nodes, int m_tiles, int groups, unsigned seed)
   p.idx0.resize(rows); p.idx1.resize(rows);
   for (int r = 0; r < rows; ++r) { p.idx0[r] = rng() % (n_nodes + 1); p.idx1[r] = rng() % (n_nodes + 1); }
   p.tile_type.resize(m_tiles);
-  for (int t = 0; t < m_tiles; ++t) p.tile_type[t] = t % groups;
+  for (int t = 0; t < m_tiles; ++t) p.tile_type[t] = (t / 4) % groups;     // constant within cluster groups of up to 4 tiles
   p.W.resize((size_t)groups * 512 * 512);
   for (auto &v : p.W) v = u(rng) * 0.0442f;
   p.S.resize((size_t)rows * 512);
@@ -129,7 +129,7 @@ static void compare(const float *got, const std::vector<double> &ref, Report &re
 }
 
 // runs L1 then DEC; returns errors of H (vs ref) in `h` and of o in `o`
-template <class M>
+template <class M, int CL = 1>
 static void run_chain(const Problem &p, const std::vector<double> *Href, const std::vector<double> *oref, int iters, int sms,
                       Report &h, Report &o, int dbg = 0) {
   const int rows = p.m_tiles * 128;
@@ -156,7 +156,7 @@ static void run_chain(const Problem &p, const std::vector<double> *Href, const s
   DecArgs d;
   memset(&d, 0, sizeof(d));
   d.H = d_H; d.b_blob = d_b2; d.num_tiles = p.m_tiles * 2; d.bd1 = d_bd1; d.Wd2 = d_w2; d.bd2 = d_bd2; d.P = p.P; d.o = d_o; d.dbg = dbg;
-  CK(launch_l1_tc<M>(a, sms, 0));
+  CK((launch_l1_tc<M, CL>(a, sms, 0)));
   CK(launch_dec_tc<M>(d, sms, 0));
   CK(cudaDeviceSynchronize());
   h = Report{0, 0, 0}; o = Report{0, 0, 0};
@@ -173,7 +173,7 @@ static void run_chain(const Problem &p, const std::vector<double> *Href, const s
     cudaEvent_t e0, e1, e2;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1)); CK(cudaEventCreate(&e2));
     CK(cudaEventRecord(e0));
-    for (int i = 0; i < iters; ++i) CK(launch_l1_tc<M>(a, sms, 0));
+    for (int i = 0; i < iters; ++i) CK((launch_l1_tc<M, CL>(a, sms, 0)));
     CK(cudaEventRecord(e1));
     for (int i = 0; i < iters; ++i) CK(launch_dec_tc<M>(d, sms, 0));
     CK(cudaEventRecord(e2));
@@ -237,8 +237,8 @@ int main(int argc, char **argv) {
   printf("device %s, %d SMs, smem/block optin %zu\n", prop.name, sms, prop.sharedMemPerBlockOptin);
   int fails = 0;
   {
-    // ---- numerics: 21 tiles of 128 edges (ragged vs the grid on purpose), 3 weight groups ---------------
-    Problem p = make_problem(1000, 21, 3, 1);
+    // ---- numerics: 20 tiles of 128 edges, 3 weight groups ---------------------------------------------
+    Problem p = make_problem(1000, 20, 3, 1);
     const int rows = p.m_tiles * 128;
     std::vector<double> Href((size_t)rows * 512), oref((size_t)rows * 2 * p.P);
     for (int r = 0; r < rows; ++r) {
@@ -274,19 +274,28 @@ int main(int argc, char **argv) {
     run_chain<Mode<KIND_BF16, 3>>(p, &Href, &oref, 0, sms, h, o); chk("H bf16x3", h, 2e-5); chk("o bf16x3", o, 2e-5);
     run_chain<Mode<KIND_TF32, 1>>(p, &Href, &oref, 0, sms, h, o); chk("H tf32", h, 5e-3); chk("o tf32", o, 5e-3);
     run_chain<Mode<KIND_BF16, 1>>(p, &Href, &oref, 0, sms, h, o); chk("H bf16", h, 4e-2); chk("o bf16", o, 4e-2);
+    run_chain<Mode<KIND_BF16, 3>, 2>(p, &Href, &oref, 0, sms, h, o); chk("H bf16x3 cl2", h, 2e-5); chk("o bf16x3 cl2", o, 2e-5);
+    run_chain<Mode<KIND_BF16, 3>, 4>(p, &Href, &oref, 0, sms, h, o); chk("H bf16x3 cl4", h, 2e-5); chk("o bf16x3 cl4", o, 2e-5);
+    run_chain<Mode<KIND_TF32, 3>, 2>(p, &Href, &oref, 0, sms, h, o); chk("H tf32x3 cl2", h, 3e-6); chk("o tf32x3 cl2", o, 3e-6);
     run_fused<Mode<KIND_BF16, 3>>(p, &oref, 0, sms, o); chk("o fused bf16x3", o, 2e-5);
     run_fused<Mode<KIND_BF16, 1>>(p, &oref, 0, sms, o); chk("o fused bf16", o, 4e-2);
   }
   if (perf && fails == 0) {
-    // ---- throughput at the config-2 size: 633 edge tiles (81 024 rows), 13 weight groups ---------------
-    Problem p = make_problem(9216, 633, 13, 2);
-    const double fl1 = 2.0 * 633 * 128 * 512 * 512, fdec = 2.0 * 633 * 256 * 128 * 256;
+    // ---- throughput at the config-2 size: 632 edge tiles (80 896 rows), 13 weight groups ---------------
+    Problem p = make_problem(9216, 632, 13, 2);
+    const double fl1 = 2.0 * 632 * 128 * 512 * 512, fdec = 2.0 * 632 * 256 * 128 * 256;
     auto pr = [&](const char *name, Report h, Report o) {
       printf("%-30s l1 %.3f ms %6.1f TFLOP/s | dec %.3f ms %6.1f TFLOP/s\n", name, h.ms, fl1 / h.ms / 1e9, o.ms, fdec / o.ms / 1e9);
     };
     Report h, o;
     run_chain<Mode<KIND_TF32, 3>>(p, nullptr, nullptr, 20, sms, h, o); pr("tf32x3", h, o);
     run_chain<Mode<KIND_BF16, 3>>(p, nullptr, nullptr, 20, sms, h, o); pr("bf16x3", h, o);
+    run_chain<Mode<KIND_BF16, 3>, 2>(p, nullptr, nullptr, 20, sms, h, o); pr("bf16x3 cluster 2", h, o);
+    run_chain<Mode<KIND_BF16, 3>, 4>(p, nullptr, nullptr, 20, sms, h, o); pr("bf16x3 cluster 4", h, o);
+    run_chain<Mode<KIND_TF32, 3>, 2>(p, nullptr, nullptr, 20, sms, h, o); pr("tf32x3 cluster 2", h, o);
+    run_chain<Mode<KIND_TF32, 3>, 4>(p, nullptr, nullptr, 20, sms, h, o); pr("tf32x3 cluster 4", h, o);
+    run_chain<Mode<KIND_BF16, 1>, 2>(p, nullptr, nullptr, 20, sms, h, o); pr("bf16 cluster 2", h, o);
+    run_chain<Mode<KIND_BF16, 1>, 4>(p, nullptr, nullptr, 20, sms, h, o); pr("bf16 cluster 4", h, o);
     run_chain<Mode<KIND_TF32, 1>>(p, nullptr, nullptr, 20, sms, h, o); pr("tf32", h, o);
     run_chain<Mode<KIND_BF16, 1>>(p, nullptr, nullptr, 20, sms, h, o); pr("bf16", h, o);
     {
@@ -306,9 +315,9 @@ int main(int argc, char **argv) {
       snprintf(nm, sizeof nm, "tf32x3 [%s]", abl[dbg]);
       run_chain<Mode<KIND_TF32, 3>>(p, nullptr, nullptr, 10, sms, h, o, dbg); pr(nm, h, o);
     }
-    for (int dbg : {1, 2, 4, 7, 8, 15}) {
+    for (int dbg : {1, 2, 4, 7, 8, 15, 16, 32, 64, 64 + 3, 16 + 3, 32 + 3}) {
       char nm[64];
-      snprintf(nm, sizeof nm, "bf16x3 [%s]", abl[dbg]);
+      snprintf(nm, sizeof nm, "bf16x3 [dbg %d]", dbg);
       run_chain<Mode<KIND_BF16, 3>>(p, nullptr, nullptr, 10, sms, h, o, dbg); pr(nm, h, o);
     }
   }

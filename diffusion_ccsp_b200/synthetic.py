@@ -78,3 +78,20 @@ def make_noise(T: int, K: int, n: int, P: int, seed: int = 123) -> torch.Tensor:
     draw + K ULA draws (reference draw order)."""
     rng = np.random.default_rng(seed)
     return torch.from_numpy(rng.standard_normal((1 + T * (1 + K), n, P), dtype=np.float32))
+
+
+def make_trained_state_dict(fixture_path: str = None) -> Dict[str, torch.Tensor]:
+    """Qualitative-mode state_dict in the REALISTIC regime: synthetic.make_state_dict(seed) with the ~74 k
+    parameters trained by tests/golden/make_trained_fixture.py (pose encoder/decoder, mlps biases; trained with
+    the reference's own loss) overlaid.  With it the sampler stays at |x| = O(1) like a real checkpoint."""
+    import os
+    if fixture_path is None:
+        fixture_path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests', 'golden',
+                                    'trained_small_qualitative.npz')
+    z = np.load(fixture_path)
+    sd = make_state_dict(DIMS['qualitative'], 'qualitative', seed=int(z['weight_seed']))
+    for k in z.files:
+        if k != 'weight_seed':
+            assert k in sd and tuple(sd[k].shape) == z[k].shape, k
+            sd[k] = torch.from_numpy(z[k].astype(np.float32))
+    return sd

@@ -53,9 +53,28 @@ def save(name, **arrs):
     print(f'{name}: {os.path.getsize(path) / 1024:.1f} KiB')
 
 
+def ula_plus_case():
+    """EBM='ULA+' (ddpm.py:297-299): 4/8/12/16 ULA steps per quarter of the schedule, low t -> high t."""
+    b = scenes.qualitative_batch(4, 3)
+    dims = synthetic.DIMS['qualitative']
+    T = 8
+    m, gd = build_reference('qualitative', dims, T, 'ULA+', 10, weight_seed=5)
+    draws = 1 + T + 2 * (4 + 8 + 12 + 16)
+    rng = np.random.default_rng(99)
+    noise = torch.from_numpy(rng.standard_normal((draws, b.num_nodes, 4), dtype=np.float32))
+    with injected_randn(noise) as inj:
+        out, hist = gd.sample(b, return_history=True)
+    assert inj.calls == draws, (inj.calls, draws)
+    hist = torch.stack([h.detach() for h in hist]).numpy()
+    save('ulaplus_qualitative_T8', out=out.detach().numpy(), history=hist, T=T, weight_seed=5, noise_seed=99,
+         input_mode='qualitative', triangular=False, **batch_arrays(b))
+
+
 def main():
     torch.set_num_threads(8)
     dfn, ddpm = load_reference()
+    if '--ulaplus-only' in sys.argv:
+        return ula_plus_case()
 
     # ---- schedule tables (ddpm.py:184-226) --------------------------------------------------
     for T in (100, 1000):
@@ -117,6 +136,7 @@ def main():
             save(f'traj_{case}_T{T}_{tag}', out=out.detach().numpy(), history=hist, T=T, K=K,
                  EBM=str(EBM), weight_seed=21, noise_seed=456, input_mode=mode, triangular=tri,
                  **batch_arrays(b))
+    ula_plus_case()
 
 
 if __name__ == '__main__':

@@ -63,3 +63,29 @@ def test_trajectory(name):
     gt = batch.x.numpy()[:, dims[-1][1]:dims[-1][2]]
     for h in hist:
         assert np.array_equal(h[m], gt[m])
+
+
+def test_ula_plus_schedule():
+    """EBM='ULA+': 4/8/12/16 ULA steps per quarter of the schedule (ddpm.py:297-299)."""
+    z, batch = load_golden('ulaplus_qualitative_T8')
+    mode, dims, sd = case_model(z)
+    den = orc.OracleDenoiser({k: v.numpy() for k, v in sd.items()}, dims, mode)
+    gd = orc.OracleDiffusion(den, timesteps=8, EBM='ULA+')
+    noise = np.random.default_rng(int(z['noise_seed'])).standard_normal((1 + 8 + 2 * 40, batch.num_nodes, 4), dtype=np.float32)
+    out, hist = gd.p_sample_loop(batch, noise, return_history=True)
+    assert rel_err(out, z['out']) < TRAJ_TOL and rel_err(np.stack(hist), z['history']) < TRAJ_TOL
+
+
+def test_trained_regime_T100():
+    """Realistic O(1) regime: weights partially trained with the reference's own loss
+    (tests/golden/make_trained_fixture.py); oracle vs the reference's trajectory."""
+    z, batch = load_golden('trained_traj_qualitative_T100')
+    dims = synthetic.DIMS['qualitative']
+    sd = synthetic.make_trained_state_dict()
+    den = orc.OracleDenoiser({k: v.numpy() for k, v in sd.items()}, dims, 'qualitative')
+    gd = orc.OracleDiffusion(den, timesteps=100, EBM='ULA', samples_per_step=10)
+    noise = synthetic.make_noise(100, 10, batch.num_nodes, 4, seed=int(z['noise_seed'])).numpy()
+    out, hist = gd.p_sample_loop(batch, noise, return_history=True)
+    assert np.abs(z['out']).max() < 2.0                      # the regime really is O(1)
+    assert rel_err(out, z['out']) < TRAJ_TOL, rel_err(out, z['out'])
+    assert rel_err(np.stack(hist)[::int(z['history_every'])], z['history']) < TRAJ_TOL
