@@ -10,6 +10,7 @@
 #include "common.cuh"
 #include "kernels_simt.cuh"
 #include "kernels_tc.cuh"
+#include "kernels_fused2.cuh"
 
 namespace ccsp {
 static thread_local std::string g_last_error;
@@ -271,7 +272,28 @@ static int ensure_mode_buffers(CcspPlan *p) {
   }
   const int kind = math_kind(m->math), elt = kind == 0 ? 4 : 2;
   if (!p->pe_split[kind]) CCSP_CUDA_TRY(p->pool.alloc(&p->pe_split[kind], (size_t)(p->n + 1) * 2 * CCSP_H * elt));
-  if (!p->Hop[m->math]) CCSP_CUDA_TRY(p->pool.alloc(&p->Hop[m->math], (size_t)p->Epad * CCSP_H2 * elt * math_ns(m->math)));
+  // BF16 operand modes run the fused CTA-pair kernel (H never leaves the SM); only the two-kernel TF32 path needs H in HBM
+  if (kind == 0 && !p->Hop[m->math]) CCSP_CUDA_TRY(p->pool.alloc(&p->Hop[m->math], (size_t)p->Epad * CCSP_H2 * elt * math_ns(m->math)));
+  return CCSP_OK;
+}
+
+static inline bool edge_fused(int math) { return math == CCSP_MATH_BF16X3 || math == CCSP_MATH_BF16; }
+
+// BF16 operand modes: first layer + decoder as ONE CTA-pair kernel (kernels_fused2.cuh)
+template <class M>
+static int launch_edge_pair(CcspPlan *p, const float *tb, cudaStream_t st) {
+  CcspModel *m = p->m;
+  tc::FusedArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.pe_split = p->pe_split[1];
+  a.src_i = p->src_i; a.src_j = p->src_j;
+  a.b_blob = m->blob_l1[m->math]; a.w_blob = m->blob_dec[m->math];
+  a.tile_type = p->tile_type;
+  a.num_m_tiles = (int)(p->Epad / CCSP_TILE_M);
+  a.S = p->S; a.tb = tb;
+  a.bd1 = m->dec_b1; a.Wd2 = m->dec_w2; a.bd2 = m->dec_b2; a.P = m->P; a.o = p->o;
+  CCSP_CUDA_TRY((tc::launch_fused2_tc<M>(a, m->num_sms, st)));
+  count_launch();
   return CCSP_OK;
 }
 
@@ -321,9 +343,9 @@ static int launch_edge(CcspPlan *p, int t, cudaStream_t st, cudaEvent_t mid = nu
       return CCSP_OK;
     }
     case CCSP_MATH_TF32X3: return launch_edge_tc<tc::Mode<tc::KIND_TF32, 3>>(p, tb, st, mid);
-    case CCSP_MATH_BF16X3: return launch_edge_tc<tc::Mode<tc::KIND_BF16, 3>>(p, tb, st, mid);
+    case CCSP_MATH_BF16X3: return launch_edge_pair<tc::Mode<tc::KIND_BF16, 3>>(p, tb, st);
     case CCSP_MATH_TF32: return launch_edge_tc<tc::Mode<tc::KIND_TF32, 1>>(p, tb, st, mid);
-    case CCSP_MATH_BF16: return launch_edge_tc<tc::Mode<tc::KIND_BF16, 1>>(p, tb, st, mid);
+    case CCSP_MATH_BF16: return launch_edge_pair<tc::Mode<tc::KIND_BF16, 1>>(p, tb, st);
     default:
       set_error("unknown math mode");
       return CCSP_ERR_STATE;
@@ -572,8 +594,12 @@ static int drain_timing(CcspPlan *p) {
   for (size_t g = 0; g + 4 <= p->ev_used; g += 4) {
     float a = 0, b = 0, c = 0;
     CCSP_CUDA_TRY(cudaEventSynchronize(p->ev[g + 3]));
-    CCSP_CUDA_TRY(cudaEventElapsedTime(&a, p->ev[g], p->ev[g + 1]));
-    CCSP_CUDA_TRY(cudaEventElapsedTime(&b, p->ev[g + 1], p->ev[g + 2]));
+    if (edge_fused(p->m->math)) {          // one edge kernel: everything between the first and third event
+      CCSP_CUDA_TRY(cudaEventElapsedTime(&a, p->ev[g], p->ev[g + 2]));
+    } else {
+      CCSP_CUDA_TRY(cudaEventElapsedTime(&a, p->ev[g], p->ev[g + 1]));
+      CCSP_CUDA_TRY(cudaEventElapsedTime(&b, p->ev[g + 1], p->ev[g + 2]));
+    }
     CCSP_CUDA_TRY(cudaEventElapsedTime(&c, p->ev[g + 2], p->ev[g + 3]));
     p->timing.samples += 1; p->timing.ms_edge_l1 += a; p->timing.ms_edge_dec += b; p->timing.ms_node += c;
   }

@@ -1,0 +1,607 @@
+// kernels_fused2.cuh — the per-edge MLP as ONE kernel on a CTA pair (tcgen05 cta_group::2), BF16 operand modes.
+//
+//   o[e, slot, :] = pose_decoder( SiLU( [pe_i ; pe_j] W_c,pose^T + S[e] + tb[t,c] )[slot half] )
+//   (denoise_fn.py:341-371 restricted to the per-call pose term; S and tb are hoisted)
+//
+// Why a CTA pair.  The ablations of the single-CTA kernels (profiles/r1e_harness_ablation.txt) show the first
+// layer limited by what one SM can ingest from L2 (~64 B/clk): per 128-edge x 256-output tile it pulls 256 KB of
+// gathered pose embeddings, 512 KB of weights and 128 KB of S against 12.3 k tensor-pipe cycles.  Multicasting the
+// weights does not help (every SM still receives all of them).  With cta_group::2 the two CTAs of a pair work on
+// two consecutive 128-edge tiles (an M = 256 MMA), and each CTA stages only HALF of every weight chunk: the
+// tensor cores of both SMs read both halves.  Weight ingest per SM halves, the shared-memory ring stages shrink
+// from 48 KB to 32 KB, and that room pays for a 4-deep ring of decoder operand chunks, so the first-layer
+// activations H never leave the SM:
+//
+//   GEMM1  D1[128 x 256] (TMEM cols 0..255)   <- gathered A (cp.async) x W_c,pose chunk (cp.async.bulk)
+//   epi-1  16 warps: D1 -> +S +tb -> SiLU -> hi/lo BF16 -> decoder operand chunks in a shared-memory ring
+//   GEMM2  D2[128 x 128] (TMEM cols 256.., double buffered) <- those chunks x pose_decoder.0 chunks
+//   epi-2  same 16 warps: D2 -> +b -> SiLU -> 128 -> P FMAs -> o
+//
+// D1 is single-buffered: GEMM1 of the next unit starts when epi-1 has pulled the last D1 columns into
+// registers; GEMM2 of the current unit fills that window on the tensor pipe.
+//
+//   warps 0-15   epilogues (warp w: TMEM lanes 32 (w & 3).., column group w >> 2)
+//   warps 16-19  A gather (cp.async 16 B pieces through the edge index)
+//   warp  20     first-layer weight loader (one lane, cp.async.bulk)
+//   warp  21     leader CTA: GEMM1 issuer.  peer CTA: relays "my stage is full" to the leader's barrier
+//   warp  22     leader CTA: GEMM2 issuer.  peer CTA: relays the decoder-weight ring likewise
+//   warp  23     decoder weight loader (one lane)
+#pragma once
+#include "kernels_tc.cuh"
+
+namespace ccsp {
+namespace tc {
+
+// ---- cluster / CTA-pair PTX wrappers ---------------------------------------------------------------
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx_remote(uint32_t cluster_addr, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_addr), "r"(bytes) : "memory");
+}
+// bulk copy whose complete_tx lands on a barrier given by its shared::cluster address (may be the peer CTA's)
+__device__ __forceinline__ void bulk_g2s_rbar(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar_cluster_addr) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar_cluster_addr) : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t *bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void prefetch_l2_bulk(const void *src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+// (CTA-scope acquire on purpose: a cluster-scope acquire costs an L1 invalidate (CCTL.IVALL) per wait, ~400 cycles in the
+// issue loops; what crosses CTAs here are barrier signals, the operand bytes are read by each SM's own tensor core.)
+__device__ __forceinline__ bool mbar_try_wait_cl(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n.reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n}"
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cl(uint64_t *bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait_cl(bar, parity)) {
+    if (++spins > SPIN_LIMIT) __trap();
+  }
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t *dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma2_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+               "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}"
+               ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// completion of all MMAs issued so far by this thread -> one arrival on the barrier at this CTA-relative
+// offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit2(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+// 32 lanes x 16 consecutive FP32 columns
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// one 64-byte k-chunk of MMAs on the pair: D[256 x N] (+)= A . B^T; every CTA contributes its 128 rows of A and
+// its N/2 rows of B, both at the same CTA-relative shared-memory offsets.  b_part = bytes of one operand part
+// (hi or lo) of this CTA's B half.
+template <class M, int NTILE>
+__device__ __forceinline__ void issue_chunk2(uint32_t d_tmem, uint32_t a_hi, uint32_t b_hi, uint32_t b_part, bool first) {
+  static_assert(M::KIND == KIND_BF16, "pair kernel is BF16-operand only");
+  constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NTILE >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+  const uint32_t a_lo = a_hi + PART, b_lo = b_hi + b_part;
+#pragma unroll
+  for (int ks = 0; ks < M::KSTEPS; ++ks) {
+    const uint32_t ko = ks * 32;
+    if (M::NSPLIT == 3) {
+      umma2_f16(d_tmem, smem_desc_sw64(a_lo + ko), smem_desc_sw64(b_hi + ko), idesc, !(first && ks == 0));
+      umma2_f16(d_tmem, smem_desc_sw64(a_hi + ko), smem_desc_sw64(b_lo + ko), idesc, 1);
+      umma2_f16(d_tmem, smem_desc_sw64(a_hi + ko), smem_desc_sw64(b_hi + ko), idesc, 1);
+    } else {
+      umma2_f16(d_tmem, smem_desc_sw64(a_hi + ko), smem_desc_sw64(b_hi + ko), idesc, !(first && ks == 0));
+    }
+  }
+}
+
+// one k-step (K = 16) of the same
+template <class M, int NTILE>
+__device__ __forceinline__ void issue_kstep2(uint32_t d_tmem, uint32_t a_hi, uint32_t b_hi, uint32_t b_part, int ks, bool zero) {
+  constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NTILE >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+  const uint32_t ko = ks * 32;
+  const uint32_t a_lo = a_hi + PART, b_lo = b_hi + b_part;
+  if (M::NSPLIT == 3) {
+    umma2_f16(d_tmem, smem_desc_sw64(a_lo + ko), smem_desc_sw64(b_hi + ko), idesc, !zero);
+    umma2_f16(d_tmem, smem_desc_sw64(a_hi + ko), smem_desc_sw64(b_lo + ko), idesc, 1);
+    umma2_f16(d_tmem, smem_desc_sw64(a_hi + ko), smem_desc_sw64(b_hi + ko), idesc, 1);
+  } else {
+    umma2_f16(d_tmem, smem_desc_sw64(a_hi + ko), smem_desc_sw64(b_hi + ko), idesc, !zero);
+  }
+}
+
+// SiLU with bare ex2/rcp approximations (what __expf/__fdividef use, minus their range fix-ups: 1 + 2^y never
+// reaches the rcp overflow range before it is +inf, where x * 0 is the right answer)
+__device__ __forceinline__ float silu_raw(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return x * r;
+}
+// (a, b) -> packed BF16 pair of the rounded values, and of the rounding residuals
+__device__ __forceinline__ void split_pair(float a, float b, uint32_t &hi, uint32_t &lo) {
+  hi = pack_bf16(a, b);
+  lo = pack_bf16(a - __uint_as_float(hi << 16), b - __uint_as_float(hi & 0xFFFF0000u));
+}
+
+template <class M>
+struct Fused2Cfg {
+  static_assert(M::KIND == KIND_BF16, "one 32-column epilogue chunk = one BF16 k-chunk of the decoder");
+  static constexpr int NT1 = 256, NT2 = 128;
+  static constexpr int B1_PART = (NT1 / 2) * ROWB;            // this CTA's 128 weight rows of one operand part: 8 KB
+  static constexpr int B1_STAGE = M::NS * B1_PART;
+  static constexpr int B1_BLOB_PART = NT1 * ROWB;             // part size in the packed blob (256 rows)
+  static constexpr int B1_BLOB_STAGE = M::NS * B1_BLOB_PART;
+  static constexpr int STAGE1 = M::A_STAGE + B1_STAGE;        // 32 KB (x3 split)
+  static constexpr int NSTAGE1 = 4;
+  static constexpr int LAG = 2;
+  static constexpr int A2_STAGE = M::A_STAGE;                 // one decoder k-chunk of 128 rows: 16 KB
+  static constexpr int NA2 = 4;                               // one stage per epilogue column group
+  static constexpr int W_PART = (NT2 / 2) * ROWB;             // this CTA's 64 decoder-weight rows of one part: 4 KB
+  static constexpr int W_STAGE = M::NS * W_PART;
+  static constexpr int W_BLOB_PART = NT2 * ROWB;
+  static constexpr int W_BLOB_STAGE = M::NS * W_BLOB_PART;
+  static constexpr int NW = 2;
+  static constexpr int OFF_A2 = NSTAGE1 * STAGE1;
+  static constexpr int OFF_W = OFF_A2 + NA2 * A2_STAGE;
+  static constexpr int OFF_EXTRA = OFF_W + NW * W_STAGE;
+  static constexpr int NUM_EPI = 16, EPI_T = NUM_EPI * 32;
+  static constexpr int WARP_PROD0 = NUM_EPI, NUM_PROD_WARPS = 4;
+  static constexpr int WARP_LOAD = 20, WARP_MMA1 = 21, WARP_MMA2 = 22, WARP_LOADW = 23;
+  static constexpr int THREADS = 24 * 32;                     // 768
+  // barriers 512 | tb_s 2x256 | bd1 128 | w2t 128x8 | bd2 16 | red 3x128 float4
+  static constexpr int SMEM_EXTRA = 512 + (512 + CCSP_HH + CCSP_MAXP * CCSP_HH + 16) * 4 + 3 * SUB_M * 16;
+  static constexpr int SMEM_BYTES = OFF_EXTRA + SMEM_EXTRA + 1024;
+  static constexpr int D2_COL = 256;
+  static_assert(SMEM_BYTES <= 227 * 1024, "pair kernel does not fit in shared memory");
+};
+
+template <class M>
+__global__ void __launch_bounds__(Fused2Cfg<M>::THREADS, 1) k_edge_fused2_tc(const FusedArgs A) {
+  using C = Fused2Cfg<M>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t *extra = smem + C::OFF_EXTRA;
+  uint64_t *full1 = reinterpret_cast<uint64_t *>(extra);     // [4] stage of ring 1 filled (leader: incl. the peer's)
+  uint64_t *empty1 = full1 + 4;                              // [4]
+  uint64_t *a2_full = empty1 + 4;                            // [4] decoder operand chunk written (leader only)
+  uint64_t *a2_empty = a2_full + 4;                          // [4][2] per 32-byte half (k-step) of a group's stage
+  uint64_t *w_full = a2_empty + 8;                           // [2]
+  uint64_t *w_empty = w_full + 2;                            // [2]
+  uint64_t *tfull1 = w_empty + 2, *tempty1 = tfull1 + 1;     // D1
+  uint64_t *tfull2 = tempty1 + 1, *tempty2 = tfull2 + 2;     // D2 [2]
+  uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(tempty2 + 2);
+  float *tb_s = reinterpret_cast<float *>(extra + 512);      // [2][256]
+  float *bd1 = tb_s + 512;                                   // [128]
+  float *w2t = bd1 + CCSP_HH;                                // [128][8]
+  float *bd2 = w2t + CCSP_MAXP * CCSP_HH;                    // [8] (+8 pad)
+  float4 *red = reinterpret_cast<float4 *>(bd2 + 16);        // [3][128]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int num_units = (A.num_m_tiles / 2) * 2;             // (pair of 128-edge tiles, slot)
+  const int unit0 = blockIdx.x >> 1, unit_step = gridDim.x >> 1;
+  const uint32_t smem_base = smem_u32(smem);
+  // (Letting the peer's cp.async.bulk complete_tx on the leader's barrier directly traps on B200: the barrier of a
+  // non-tensor bulk copy has to live in the destination CTA.  Hence the relay lanes.)
+  constexpr bool direct = false;
+  long long *const tr = (A.trace && blockIdx.x == 0) ? A.trace : nullptr;
+#define TR(role, slot) do { if (tr && it < 8) tr[((role) * 8 + it) * 16 + (slot)] = clock64(); } while (0)
+#define TRP(role, slot) do { if (tr && itp < 8) tr[((role) * 8 + itp) * 16 + (slot)] = clock64(); } while (0)
+
+  if (threadIdx.x == 0) {
+    // ring 1: own gather threads + own weight loader (+ at the leader: the peer's relay lane)
+    for (int s = 0; s < C::NSTAGE1; ++s) { mbar_init(&full1[s], C::NUM_PROD_WARPS * 32 + 1 + (leader ? 1 : 0)); mbar_init(&empty1[s], 1); }
+    for (int s = 0; s < C::NA2; ++s) { mbar_init(&a2_full[s], 8); mbar_init(&a2_empty[2 * s], 1); mbar_init(&a2_empty[2 * s + 1], 1); }
+    for (int s = 0; s < C::NW; ++s) { mbar_init(&w_full[s], leader ? 2 : 1); mbar_init(&w_empty[s], 1); }
+    mbar_init(tfull1, 1); mbar_init(tempty1, 2 * C::NUM_EPI);
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull2[b], 1); mbar_init(&tempty2[b], 2 * C::NUM_EPI); }
+    fence_barrier_init();
+  }
+  if (warp == C::WARP_MMA1) tmem_alloc2(tmem_ptr, 512);
+  if (warp < C::NUM_EPI) {
+    for (int i = threadIdx.x; i < CCSP_HH; i += C::EPI_T) bd1[i] = A.bd1[i];
+    for (int i = threadIdx.x; i < CCSP_MAXP * CCSP_HH; i += C::EPI_T) {
+      const int j = i / CCSP_MAXP, pp = i % CCSP_MAXP;
+      w2t[i] = pp < A.P ? A.Wd2[pp * CCSP_HH + j] : 0.f;
+    }
+    if (threadIdx.x < CCSP_MAXP) bd2[threadIdx.x] = threadIdx.x < A.P ? A.bd2[threadIdx.x] : 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();                      // both CTAs' barriers are initialised before any remote arrival / multicast commit
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp >= C::WARP_PROD0 && warp < C::WARP_PROD0 + C::NUM_PROD_WARPS) {
+    // ============ A gather: this CTA's 128 edges; thread = (piece q, rows r0 + 32 p) ==================
+    const int t = threadIdx.x - C::WARP_PROD0 * 32;
+    const int q = t & 3, r0 = t >> 2;
+    // Completion is signalled by the copy engine itself (cp.async.mbarrier.arrive.noinc: one arrival per thread
+    // when all its earlier cp.async have landed), so a thread never waits for data and all NSTAGE1 stages can be
+    // in flight; the peer's barrier is forwarded to the leader by the relay lane below.
+    uint32_t g = 0, it = 0;
+    for (int u = unit0; u < num_units; u += unit_step, ++it) {
+      const int m0 = ((u >> 1) * 2 + (int)rank) * SUB_M;
+      size_t roff[4];
+#pragma unroll 1
+      for (int kc = 0; kc < M::NKC1; ++kc, ++g) {
+        if (kc == 0 || kc == M::NKC1 / 2) {
+          const int *idx = kc == 0 ? A.src_i : A.src_j;
+#pragma unroll
+          for (int p = 0; p < 4; ++p) roff[p] = (size_t)__ldg(&idx[m0 + r0 + 32 * p]) * M::PE_ROW_BYTES;
+        }
+        const uint32_t s = g % C::NSTAGE1;
+        mbar_wait(&empty1[s], ((g / C::NSTAGE1) & 1) ^ 1);
+        if (t == 0) TR(6, kc);
+        if (!(A.dbg & 1)) {
+          const uint32_t koff = (uint32_t)(kc % (M::NKC1 / 2)) * ROWB + q * 16;
+          const uint32_t st = smem_base + s * C::STAGE1;
+#pragma unroll
+          for (int p = 0; p < 4; ++p) {
+            const uint8_t *src = A.pe_split + roff[p] + koff;
+            const uint32_t dst = st + sw64_off(r0 + 32 * p, q);
+            cp_async16(dst, src);
+            if (M::NS == 2) cp_async16(dst + PART, src + M::PE_LO_OFF);
+          }
+        }
+        cp_async_arrive_noinc(&full1[s]);
+        if (t == 0) TR(7, kc);
+      }
+    }
+  } else if (warp == C::WARP_LOAD) {
+    if (lane == 0) {
+      // ============ first-layer weights: this CTA's 128 of the 256 rows of every chunk =================
+      uint32_t g = 0;
+      for (int u = unit0; u < num_units; u += unit_step) {
+        const int mt = (u >> 1) * 2, slot = u & 1;
+        const int grp = __ldg(&A.tile_type[mt]);
+        const uint8_t *blob = A.b_blob + ((size_t)(grp * 2 + slot) * M::NKC1) * C::B1_BLOB_STAGE + rank * C::B1_PART;
+        for (int kc = 0; kc < M::NKC1; ++kc, ++g) {
+          const uint32_t s = g % C::NSTAGE1;
+          mbar_wait(&empty1[s], ((g / C::NSTAGE1) & 1) ^ 1);
+          // direct mode: the copy's complete_tx lands on the LEADER's barrier; relay mode: on the local one
+          const uint32_t bar = direct ? mapa_u32(smem_u32(&full1[s]), 0) : smem_u32(&full1[s]);
+          if (A.dbg & 2) { mbar_arrive_remote(bar); continue; }
+          mbar_arrive_expect_tx_remote(bar, C::B1_STAGE);
+          const uint32_t dst = smem_base + s * C::STAGE1 + M::A_STAGE;
+          const uint8_t *src = blob + (size_t)kc * C::B1_BLOB_STAGE;
+          bulk_g2s_rbar(dst, src, C::B1_PART, bar);
+          if (M::NS == 2) bulk_g2s_rbar(dst + C::B1_PART, src + C::B1_BLOB_PART, C::B1_PART, bar);
+        }
+      }
+    }
+  } else if (warp == C::WARP_LOADW) {
+    // (own warp: a lane that sleeps in mbarrier.try_wait holds up the other lanes of its warp)
+    if (lane == 0) {
+      // ============ decoder weights: this CTA's 64 of the 128 rows, chunks in GEMM2's consumption order ==
+      uint32_t g2 = 0;
+      const uint8_t *blob = A.w_blob + rank * C::W_PART;
+      for (int u = unit0; u < num_units; u += unit_step) {
+        for (int q = 0; q < 8; ++q, ++g2) {
+          const uint32_t s = g2 % C::NW;
+          mbar_wait(&w_empty[s], ((g2 / C::NW) & 1) ^ 1);
+          const uint32_t bar = direct ? mapa_u32(smem_u32(&w_full[s]), 0) : smem_u32(&w_full[s]);
+          if (A.dbg & 2) { mbar_arrive_remote(bar); continue; }
+          const int c = 2 * (q & 3) + (q >> 2);
+          mbar_arrive_expect_tx_remote(bar, C::W_STAGE);
+          const uint32_t dst = smem_base + C::OFF_W + s * C::W_STAGE;
+          const uint8_t *src = blob + (size_t)c * C::W_BLOB_STAGE;
+          bulk_g2s_rbar(dst, src, C::W_PART, bar);
+          if (M::NS == 2) bulk_g2s_rbar(dst + C::W_PART, src + C::W_BLOB_PART, C::W_PART, bar);
+        }
+      }
+    }
+  } else if (warp == C::WARP_MMA1) {
+    if (lane == 0) {
+      if (leader) {
+        // ============ GEMM1 issuer (M = 256 over the pair) =============================================
+        uint32_t g = 0, it = 0;
+        for (int u = unit0; u < num_units; u += unit_step, ++it) {
+          TR(0, 0);
+          mbar_wait_cl(tempty1, (it & 1) ^ 1);
+          TR(0, 1);
+          tc_fence_after();
+          for (int kc = 0; kc < M::NKC1; ++kc, ++g) {
+            const uint32_t s = g % C::NSTAGE1;
+            mbar_wait_cl(&full1[s], (g / C::NSTAGE1) & 1);
+            if (kc == 0) TR(0, 2);
+            if (kc == 8) TR(0, 3);
+            TR(4, kc);
+            tc_fence_after();
+            const uint32_t a_hi = smem_base + s * C::STAGE1;
+            if (!(A.dbg & 8)) issue_chunk2<M, C::NT1>(tmem_base, a_hi, a_hi + M::A_STAGE, C::B1_PART, kc == 0);
+            umma_commit2(&empty1[s]);
+            TR(5, kc);
+          }
+          umma_commit2(tfull1);
+          TR(0, 4);
+        }
+      } else {
+        // ============ peer: forward "stage s is full here (A rows + weight half)" to the leader ==========
+        uint32_t g = 0;
+        uint32_t rfull[C::NSTAGE1];
+#pragma unroll
+        for (int s = 0; s < C::NSTAGE1; ++s) rfull[s] = mapa_u32(smem_u32(&full1[s]), 0);
+        for (int u = unit0; u < num_units; u += unit_step) {
+          for (int kc = 0; kc < M::NKC1; ++kc, ++g) {
+            const uint32_t s = g % C::NSTAGE1;
+            mbar_wait(&full1[s], (g / C::NSTAGE1) & 1);
+            mbar_arrive_remote(rfull[s]);
+          }
+        }
+      }
+    }
+  } else if (warp == C::WARP_MMA2) {
+    if (lane == 0) {
+      if (leader) {
+        // ============ GEMM2 issuer ======================================================================
+        uint32_t g2 = 0, it = 0;
+        for (int u = unit0; u < num_units; u += unit_step, ++it) {
+          const uint32_t buf = it & 1;
+          TR(1, 0);
+          mbar_wait_cl(&tempty2[buf], ((it >> 1) & 1) ^ 1);
+          TR(1, 1);
+          tc_fence_after();
+          for (int q = 0; q < 8; ++q, ++g2) {
+            const uint32_t cg = q & 3, uu = it * 2 + (q >> 2), ws = g2 % C::NW;
+            mbar_wait_cl(&a2_full[cg], uu & 1);
+            if (q == 0) TR(1, 2);
+            if (q == 4) TR(1, 4);
+            mbar_wait_cl(&w_full[ws], (g2 / C::NW) & 1);
+            if (q == 0) TR(1, 3);
+            if (q == 4) TR(1, 5);
+            tc_fence_after();
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {       // each 32-byte half of the group's stage is released on its own
+              if (!(A.dbg & 8))
+                issue_kstep2<M, C::NT2>(tmem_base + C::D2_COL + buf * C::NT2, smem_base + C::OFF_A2 + cg * C::A2_STAGE,
+                                        smem_base + C::OFF_W + ws * C::W_STAGE, C::W_PART, ks, q == 0 && ks == 0);
+              umma_commit2(&a2_empty[2 * cg + ks]);
+            }
+            umma_commit2(&w_empty[ws]);
+          }
+          umma_commit2(&tfull2[buf]);
+          TR(1, 6);
+        }
+      } else {
+        uint32_t g2 = 0;
+        uint32_t rfull[C::NW];
+#pragma unroll
+        for (int s = 0; s < C::NW; ++s) rfull[s] = mapa_u32(smem_u32(&w_full[s]), 0);
+        for (int u = unit0; u < num_units; u += unit_step) {
+          for (int q = 0; q < 8; ++q, ++g2) {
+            const uint32_t s = g2 % C::NW;
+            mbar_wait(&w_full[s], (g2 / C::NW) & 1);
+            mbar_arrive_remote(rfull[s]);
+          }
+        }
+      }
+    }
+  } else if (warp < C::NUM_EPI) {
+    // ============ epilogues: warp w <-> TMEM lanes 32 (w & 3).., column group cg = w >> 2 =================
+    const int quarter = warp & 3, cg = warp >> 2;
+    const int r = quarter * 32 + lane;
+    uint8_t *a2_stage = smem + C::OFF_A2 + cg * C::A2_STAGE;
+    const uint32_t r_tempty1 = mapa_u32(smem_u32(tempty1), 0);
+    const uint32_t r_tempty2_0 = mapa_u32(smem_u32(&tempty2[0]), 0), r_tempty2_1 = mapa_u32(smem_u32(&tempty2[1]), 0);
+    const uint32_t r_a2_full = mapa_u32(smem_u32(&a2_full[cg]), 0);
+    // ---- epilogue-2 of unit itp (deferred by one unit: GEMM2 had a whole GEMM1 to finish): D2 -> o -------
+    auto epi2 = [&](uint32_t itp, size_t rowp, int slotp) {
+      const int trole = warp == 0 ? 2 : 3;
+      const bool tron = lane == 0 && (warp == 0 || warp == 12);
+      const uint32_t buf = itp & 1;
+      if (tron) TRP(trole, 7);
+      mbar_wait_cl(&tfull2[buf], (itp >> 1) & 1);
+      if (tron) TRP(trole, 8);
+      tc_fence_after();
+      const uint32_t taddr2 = tmem_base + C::D2_COL + buf * C::NT2 + cg * 32 + ((uint32_t)(quarter * 32) << 16);
+      float acc[CCSP_MAXP];
+#pragma unroll
+      for (int p = 0; p < CCSP_MAXP; ++p) acc[p] = 0.f;
+#pragma unroll 1
+      for (int hc = 0; hc < 2; ++hc) {
+        float v[16];
+        tmem_ld16(taddr2 + hc * 16, v);
+        if (hc == 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_remote(buf ? r_tempty2_1 : r_tempty2_0);
+        }
+        const int c0 = cg * 32 + hc * 16;
+        if (A.P <= 4) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float d = silu_raw(v[j] + bd1[c0 + j]);
+            const float4 w = *reinterpret_cast<const float4 *>(&w2t[(c0 + j) * CCSP_MAXP]);
+            acc[0] = fmaf(d, w.x, acc[0]); acc[1] = fmaf(d, w.y, acc[1]); acc[2] = fmaf(d, w.z, acc[2]); acc[3] = fmaf(d, w.w, acc[3]);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float d = silu_raw(v[j] + bd1[c0 + j]);
+            const float4 w0 = *reinterpret_cast<const float4 *>(&w2t[(c0 + j) * CCSP_MAXP]);
+            const float4 w1 = *reinterpret_cast<const float4 *>(&w2t[(c0 + j) * CCSP_MAXP + 4]);
+            acc[0] = fmaf(d, w0.x, acc[0]); acc[1] = fmaf(d, w0.y, acc[1]); acc[2] = fmaf(d, w0.z, acc[2]); acc[3] = fmaf(d, w0.w, acc[3]);
+            acc[4] = fmaf(d, w1.x, acc[4]); acc[5] = fmaf(d, w1.y, acc[5]); acc[6] = fmaf(d, w1.z, acc[6]); acc[7] = fmaf(d, w1.w, acc[7]);
+          }
+        }
+      }
+      if (tron) TRP(trole, 9);
+      // column groups 1..3 hand their partial sums to group 0 (fixed order -> deterministic)
+      float *orow = A.o + ((size_t)rowp * 2 + slotp) * A.P;
+      if (cg > 0) red[(cg - 1) * SUB_M + r] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      asm volatile("bar.sync 2, 512;" ::: "memory");
+      if (cg == 0 && !(A.dbg & 4)) {
+        const float4 r1 = red[r], r2 = red[SUB_M + r], r3 = red[2 * SUB_M + r];
+        float res[4] = {((acc[0] + r1.x) + r2.x) + r3.x + bd2[0], ((acc[1] + r1.y) + r2.y) + r3.y + bd2[1],
+                        ((acc[2] + r1.z) + r2.z) + r3.z + bd2[2], ((acc[3] + r1.w) + r2.w) + r3.w + bd2[3]};
+        if (A.P == 4) {
+          *reinterpret_cast<float4 *>(orow) = make_float4(res[0], res[1], res[2], res[3]);
+        } else {
+#pragma unroll
+          for (int p = 0; p < 4; ++p)
+            if (p < A.P) orow[p] = res[p];
+        }
+      }
+      if (tron) TRP(trole, 10);
+      if (A.P > 4) {                                // second round for components 4..7 (robot poses, P = 5)
+        asm volatile("bar.sync 2, 512;" ::: "memory");
+        if (cg > 0) red[(cg - 1) * SUB_M + r] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+        asm volatile("bar.sync 2, 512;" ::: "memory");
+        if (cg == 0 && !(A.dbg & 4)) {
+          const float4 r1 = red[r], r2 = red[SUB_M + r], r3 = red[2 * SUB_M + r];
+          float res[4] = {((acc[4] + r1.x) + r2.x) + r3.x + bd2[4], ((acc[5] + r1.y) + r2.y) + r3.y + bd2[5],
+                          ((acc[6] + r1.z) + r2.z) + r3.z + bd2[6], ((acc[7] + r1.w) + r2.w) + r3.w + bd2[7]};
+#pragma unroll
+          for (int p = 0; p < 4; ++p)
+            if (4 + p < A.P) orow[4 + p] = res[p];
+        }
+      }
+    };
+    size_t prev_row = 0;
+    int prev_slot = 0;
+    uint32_t it = 0;
+    for (int u = unit0; u < num_units; u += unit_step, ++it) {
+      const int mt = (u >> 1) * 2 + (int)rank, slot = u & 1;
+      const int grp = __ldg(&A.tile_type[mt]);
+      const size_t row = (size_t)mt * SUB_M + r;
+      const int gcol0 = slot * 256 + cg * 64;
+      // S in the blocked layout: 32-row x 32-col blocks of 8 pieces x 32 lanes x 16 B (coalesced 512 B / instruction)
+      const float4 *Sblk = reinterpret_cast<const float4 *>(A.S) + (((row >> 5) * 16 + (gcol0 >> 5)) * 8) * 32 + lane;
+      const bool noS = (A.dbg & 4) != 0;
+      float4 sa = noS ? make_float4(0.f, 0.f, 0.f, 0.f) : ldg_nc_f4(Sblk), sb = noS ? sa : ldg_nc_f4(Sblk + 32);
+      if (threadIdx.x < 4 && u + unit_step < num_units && !(A.dbg & 4)) {
+        // next unit's slice of S (4 row blocks x 32 KB contiguous) -> L2, so the register prefetch below only
+        // has to cover an L2 hit
+        const int un = u + unit_step;
+        const size_t rb = (size_t)((un >> 1) * 2 + (int)rank) * 4 + threadIdx.x;
+        prefetch_l2_bulk(A.S + (rb * 16 + (size_t)(un & 1) * 8) * 1024, 32768);
+      }
+      float *tbu = tb_s + (it & 1) * 256;
+      if (threadIdx.x < 256) tbu[threadIdx.x] = __ldg(&A.tb[(size_t)grp * CCSP_H2 + slot * 256 + threadIdx.x]);
+      const int trole = warp == 0 ? 2 : 3;
+      const bool tron = lane == 0 && (warp == 0 || warp == 12);
+      if (tron) TR(trole, 0);
+      asm volatile("bar.sync 1, 512;" ::: "memory");
+      if (tron) TR(trole, 1);
+      // ---- epilogue-1: D1 -> decoder operand chunks -------------------------------------------------
+      mbar_wait_cl(tfull1, it & 1);
+      if (tron) TR(trole, 2);
+      tc_fence_after();
+      const uint32_t taddr1 = tmem_base + cg * 64 + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {         // 32 columns = one decoder k-chunk
+        float v[32];
+        tmem_ld32(taddr1 + half * 32, v);
+        if (half == 1) {                             // D1 fully in registers: GEMM1 of the next unit may overwrite it
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_remote(r_tempty1);
+        }
+        if (tron) TR(trole, 3 + 2 * half);
+#pragma unroll
+        for (int pc = 0; pc < 4; ++pc) {             // 8 columns -> one 16-byte piece of hi and of lo
+          const int pi = half * 4 + pc;
+          const float4 ca = sa, cb = sb;
+          if (pi < 7 && !noS) {                      // S of the next piece, one step ahead
+            const float4 *nx = Sblk + ((pi + 1) >> 2) * 256 + ((pi + 1) & 3) * 64;
+            sa = ldg_nc_f4(nx); sb = ldg_nc_f4(nx + 32);
+          }
+          const float4 ta = *reinterpret_cast<const float4 *>(&tbu[cg * 64 + pi * 8]);
+          const float4 tb4 = *reinterpret_cast<const float4 *>(&tbu[cg * 64 + pi * 8 + 4]);
+          float f[8];
+          f[0] = silu_raw(v[pc * 8 + 0] + ca.x + ta.x); f[1] = silu_raw(v[pc * 8 + 1] + ca.y + ta.y);
+          f[2] = silu_raw(v[pc * 8 + 2] + ca.z + ta.z); f[3] = silu_raw(v[pc * 8 + 3] + ca.w + ta.w);
+          f[4] = silu_raw(v[pc * 8 + 4] + cb.x + tb4.x); f[5] = silu_raw(v[pc * 8 + 5] + cb.y + tb4.y);
+          f[6] = silu_raw(v[pc * 8 + 6] + cb.z + tb4.z); f[7] = silu_raw(v[pc * 8 + 7] + cb.w + tb4.w);
+          uint4 hi, lo;
+          split_pair(f[0], f[1], hi.x, lo.x); split_pair(f[2], f[3], hi.y, lo.y);
+          split_pair(f[4], f[5], hi.z, lo.z); split_pair(f[6], f[7], hi.w, lo.w);
+          // GEMM2 is done with this 32-byte half (k-step) of the group's stage
+          if ((pc & 1) == 0) mbar_wait(&a2_empty[2 * cg + (pc >> 1)], ((it * 2 + half) & 1) ^ 1);
+          uint8_t *dst = a2_stage + sw64_off(r, pc);
+          *reinterpret_cast<uint4 *>(dst) = hi;
+          if (M::NS == 2) *reinterpret_cast<uint4 *>(dst + PART) = lo;
+        }
+        fence_proxy_async();                         // chunk complete: publish to the async proxy, tell the leader
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote(r_a2_full);
+        if (tron) TR(trole, 4 + 2 * half);
+      }
+      if (it > 0) epi2(it - 1, prev_row, prev_slot);
+      prev_row = row; prev_slot = slot;
+    }
+    if (it > 0) epi2(it - 1, prev_row, prev_slot);
+  }
+#undef TR
+#undef TRP
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();                      // no CTA exits (or frees TMEM) while its peer may still signal it or read its operands
+  if (warp == C::WARP_MMA1) tmem_dealloc2(tmem_base, 512);
+}
+
+template <class M>
+cudaError_t launch_fused2_tc(const FusedArgs &a, int num_sms, cudaStream_t st) {
+  using C = Fused2Cfg<M>;
+  static int max_clusters = 0;
+  if (max_clusters == 0) {
+    cudaError_t e = cudaFuncSetAttribute(k_edge_fused2_tc<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    cudaLaunchConfig_t q = {};
+    q.gridDim = dim3(num_sms / 2 * 2); q.blockDim = dim3(C::THREADS); q.dynamicSmemBytes = C::SMEM_BYTES;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    q.attrs = at; q.numAttrs = 1;
+    int n = 0;
+    e = cudaOccupancyMaxActiveClusters(&n, k_edge_fused2_tc<M>, &q);
+    if (e != cudaSuccess) return e;
+    max_clusters = (n > 0 && n < num_sms / 2) ? n : num_sms / 2;
+  }
+  if (a.num_m_tiles % 2 != 0) return cudaErrorInvalidValue;
+  const int units = a.num_m_tiles;                 // (num_m_tiles / 2) pairs x 2 slots
+  if (units == 0) return cudaSuccess;
+  const int nclusters = units < max_clusters ? units : max_clusters;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(nclusters * 2); cfg.blockDim = dim3(C::THREADS); cfg.dynamicSmemBytes = C::SMEM_BYTES; cfg.stream = st;
+  cudaLaunchAttribute attrs[1];
+  attrs[0].id = cudaLaunchAttributeClusterDimension;
+  attrs[0].val.clusterDim.x = 2; attrs[0].val.clusterDim.y = 1; attrs[0].val.clusterDim.z = 1;
+  cfg.attrs = attrs; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, k_edge_fused2_tc<M>, a);
+}
+
+}  // namespace tc
+}  // namespace ccsp

@@ -712,6 +712,7 @@ struct FusedArgs {
   int P;
   float *o;                  // [Epad][2][P]
   int dbg;
+  long long *trace;          // harness only: clock64 timeline of CTA 0 ([role][unit < 8][16]), else nullptr
 };
 
 template <class M>

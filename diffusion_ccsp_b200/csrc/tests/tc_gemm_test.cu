@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "../kernels_tc.cuh"
+#include "../kernels_fused2.cuh"
 
 namespace ccsp {
 void set_error(const std::string &) {}
@@ -186,8 +187,10 @@ static void run_chain(const Problem &p, const std::vector<double> *Href, const s
   cudaFree(d_w2); cudaFree(d_bd2); cudaFree(d_o); cudaFree(d_i0); cudaFree(d_i1); cudaFree(d_tt);
 }
 
-// fused kernel: o only
-template <class M>
+static int g_dbg_or = 0;
+static bool g_trace = false;   // OR'ed into the pair kernel's dbg word (256: relay mode)
+// fused kernels: o only (PAIR: CTA-pair / cta_group::2 version)
+template <class M, bool PAIR = false>
 static void run_fused(const Problem &p, const std::vector<double> *oref, int iters, int sms, Report &o, int dbg = 0) {
   const int rows = p.m_tiles * 128;
   std::vector<float> Sblk((size_t)rows * 512);
@@ -206,9 +209,30 @@ static void run_fused(const Problem &p, const std::vector<double> *oref, int ite
   FusedArgs a;
   memset(&a, 0, sizeof(a));
   a.pe_split = d_pe; a.src_i = d_i0; a.src_j = d_i1; a.b_blob = d_b1; a.w_blob = d_b2; a.tile_type = d_tt; a.num_m_tiles = p.m_tiles;
-  a.S = d_S; a.tb = d_tb; a.bd1 = d_bd1; a.Wd2 = d_w2; a.bd2 = d_bd2; a.P = p.P; a.o = d_o; a.dbg = dbg;
-  CK(launch_fused_tc<M>(a, sms, 0));
+  a.S = d_S; a.tb = d_tb; a.bd1 = d_bd1; a.Wd2 = d_w2; a.bd2 = d_bd2; a.P = p.P; a.o = d_o; a.dbg = dbg | (PAIR ? g_dbg_or : 0);
+  long long *d_tr = nullptr;
+  if (PAIR && g_trace) {
+    CK(cudaMalloc(&d_tr, 8 * 8 * 16 * sizeof(long long)));
+    CK(cudaMemset(d_tr, 0, 8 * 8 * 16 * sizeof(long long)));
+    a.trace = d_tr;
+  }
+  CK((PAIR ? launch_fused2_tc<M>(a, sms, 0) : launch_fused_tc<M>(a, sms, 0)));
   CK(cudaDeviceSynchronize());
+  if (d_tr) {
+    std::vector<long long> tr(8 * 8 * 16);
+    CK(cudaMemcpy(tr.data(), d_tr, tr.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    const char *names[8] = {"MMA1", "MMA2", "EPI w0", "EPI w12", "M1 wait", "M1 cmt", "G empty", "G issue"};
+    long long t0 = tr[0];
+    printf("trace (dbg %d), cycles relative to MMA1 unit-0 start; columns = trace slots\n", a.dbg);
+    for (int role = 0; role < 8; ++role)
+      for (int it = (role < 4 ? 0 : 3); it < (role < 4 ? 8 : 5); ++it) {
+        printf("  %-7s u%d:", names[role], it);
+        for (int sl = 0; sl < (role < 4 ? 11 : 16); ++sl) { long long v = tr[(role * 8 + it) * 16 + sl]; if (v) printf(" %7lld", v - t0); else printf("       -"); }
+        printf("\n");
+      }
+    a.trace = nullptr;
+    cudaFree(d_tr);
+  }
   o = Report{0, 0, 0};
   if (oref) {
     std::vector<float> oo((size_t)rows * 2 * p.P);
@@ -219,7 +243,7 @@ static void run_fused(const Problem &p, const std::vector<double> *oref, int ite
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     CK(cudaEventRecord(e0));
-    for (int i = 0; i < iters; ++i) CK(launch_fused_tc<M>(a, sms, 0));
+    for (int i = 0; i < iters; ++i) CK((PAIR ? launch_fused2_tc<M>(a, sms, 0) : launch_fused_tc<M>(a, sms, 0)));
     CK(cudaEventRecord(e1));
     CK(cudaEventSynchronize(e1));
     float ms;
@@ -230,7 +254,10 @@ static void run_fused(const Problem &p, const std::vector<double> *oref, int ite
 }
 
 int main(int argc, char **argv) {
-  const bool perf = argc > 1 && !strcmp(argv[1], "perf");
+  const bool pair_only = argc > 1 && !strncmp(argv[1], "pair", 4);
+  if (argc > 1 && !strcmp(argv[1], "pairdirect")) g_dbg_or = 256;
+  g_trace = argc > 2 && !strcmp(argv[2], "trace");     // only the CTA-pair fused kernel (numerics + perf)
+  const bool perf = argc > 1 && (!strcmp(argv[1], "perf") || pair_only);
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, 0));
   const int sms = prop.multiProcessorCount;
@@ -270,6 +297,7 @@ int main(int argc, char **argv) {
       if (!ok) ++fails;
     };
     Report h, o;
+    if (!pair_only) {
     run_chain<Mode<KIND_TF32, 3>>(p, &Href, &oref, 0, sms, h, o); chk("H tf32x3", h, 3e-6); chk("o tf32x3", o, 3e-6);
     run_chain<Mode<KIND_BF16, 3>>(p, &Href, &oref, 0, sms, h, o); chk("H bf16x3", h, 2e-5); chk("o bf16x3", o, 2e-5);
     run_chain<Mode<KIND_TF32, 1>>(p, &Href, &oref, 0, sms, h, o); chk("H tf32", h, 5e-3); chk("o tf32", o, 5e-3);
@@ -279,6 +307,9 @@ int main(int argc, char **argv) {
     run_chain<Mode<KIND_TF32, 3>, 2>(p, &Href, &oref, 0, sms, h, o); chk("H tf32x3 cl2", h, 3e-6); chk("o tf32x3 cl2", o, 3e-6);
     run_fused<Mode<KIND_BF16, 3>>(p, &oref, 0, sms, o); chk("o fused bf16x3", o, 2e-5);
     run_fused<Mode<KIND_BF16, 1>>(p, &oref, 0, sms, o); chk("o fused bf16", o, 4e-2);
+    }
+    run_fused<Mode<KIND_BF16, 3>, true>(p, &oref, 0, sms, o); chk("o pair bf16x3", o, 2e-5);
+    run_fused<Mode<KIND_BF16, 1>, true>(p, &oref, 0, sms, o); chk("o pair bf16", o, 4e-2);
   }
   if (perf && fails == 0) {
     // ---- throughput at the config-2 size: 632 edge tiles (80 896 rows), 13 weight groups ---------------
@@ -288,6 +319,18 @@ int main(int argc, char **argv) {
       printf("%-30s l1 %.3f ms %6.1f TFLOP/s | dec %.3f ms %6.1f TFLOP/s\n", name, h.ms, fl1 / h.ms / 1e9, o.ms, fdec / o.ms / 1e9);
     };
     Report h, o;
+    if (pair_only) {
+      Report f;
+      const double ff = fl1 + fdec;
+      run_fused<Mode<KIND_BF16, 3>, true>(p, nullptr, 20, sms, f); printf("%-30s fused %.3f ms %6.1f TFLOP/s\n", "bf16x3 pair", f.ms, ff / f.ms / 1e9);
+      run_fused<Mode<KIND_BF16, 1>, true>(p, nullptr, 20, sms, f); printf("%-30s fused %.3f ms %6.1f TFLOP/s\n", "bf16 pair", f.ms, ff / f.ms / 1e9);
+      for (int dbg : {1, 2, 4, 7, 8, 15}) {
+        run_fused<Mode<KIND_BF16, 3>, true>(p, nullptr, 10, sms, f, dbg);
+        printf("bf16x3 pair dbg=%-2d               fused %.3f ms %6.1f TFLOP/s\n", dbg, f.ms, ff / f.ms / 1e9);
+      }
+      printf(fails ? "RESULT: FAIL (%d)\n" : "RESULT: PASS\n", fails);
+      return fails ? 1 : 0;
+    }
     run_chain<Mode<KIND_TF32, 3>>(p, nullptr, nullptr, 20, sms, h, o); pr("tf32x3", h, o);
     run_chain<Mode<KIND_BF16, 3>>(p, nullptr, nullptr, 20, sms, h, o); pr("bf16x3", h, o);
     run_chain<Mode<KIND_BF16, 3>, 2>(p, nullptr, nullptr, 20, sms, h, o); pr("bf16x3 cluster 2", h, o);
@@ -303,6 +346,12 @@ int main(int argc, char **argv) {
       const double ff = fl1 + fdec;
       run_fused<Mode<KIND_BF16, 3>>(p, nullptr, 20, sms, f); printf("%-30s fused %.3f ms %6.1f TFLOP/s\n", "bf16x3 fused", f.ms, ff / f.ms / 1e9);
       run_fused<Mode<KIND_BF16, 1>>(p, nullptr, 20, sms, f); printf("%-30s fused %.3f ms %6.1f TFLOP/s\n", "bf16 fused", f.ms, ff / f.ms / 1e9);
+      run_fused<Mode<KIND_BF16, 3>, true>(p, nullptr, 20, sms, f); printf("%-30s fused %.3f ms %6.1f TFLOP/s\n", "bf16x3 pair", f.ms, ff / f.ms / 1e9);
+      run_fused<Mode<KIND_BF16, 1>, true>(p, nullptr, 20, sms, f); printf("%-30s fused %.3f ms %6.1f TFLOP/s\n", "bf16 pair", f.ms, ff / f.ms / 1e9);
+      for (int dbg : {1, 2, 4, 7, 8, 15}) {
+        run_fused<Mode<KIND_BF16, 3>, true>(p, nullptr, 10, sms, f, dbg);
+        printf("bf16x3 pair dbg=%-2d               fused %.3f ms %6.1f TFLOP/s\n", dbg, f.ms, ff / f.ms / 1e9);
+      }
       for (int dbg : {1, 2, 4, 7, 8, 15}) {
         run_fused<Mode<KIND_BF16, 3>>(p, nullptr, 10, sms, f, dbg);
         printf("bf16x3 fused dbg=%-2d              fused %.3f ms %6.1f TFLOP/s\n", dbg, f.ms, ff / f.ms / 1e9);
