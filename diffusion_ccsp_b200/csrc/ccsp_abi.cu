@@ -11,6 +11,7 @@
 #include "kernels_simt.cuh"
 #include "kernels_tc.cuh"
 #include "kernels_fused2.cuh"
+#include "kernels_node_tc.cuh"
 
 namespace ccsp {
 static thread_local std::string g_last_error;
@@ -102,6 +103,8 @@ struct CcspModel {
   int num_sms = 148;
   std::vector<float> h_pose_w;    // [C][512][512] pose columns of mlps[c].weight, reference [out][k] layout
   std::vector<float> h_dec_w1;    // [128][256]
+  std::vector<float> h_pose_w2;   // [256][128] pose_encoder.2.weight (B operand of the tcgen05 node kernel)
+  uint8_t *blob_pose[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   uint8_t *blob_l1[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   uint8_t *blob_dec[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
 };
@@ -156,6 +159,7 @@ static int model_build(CcspModel *m, const CcspModelDesc *d) {
   if (m->Gr > 0)
     if ((rc = upload_encoder(m, m->grasp, d->grasp_w0, d->grasp_b0, d->grasp_w2, d->grasp_b2, m->Gr))) return rc;
   if ((rc = upload_encoder(m, m->pose, d->pose_w0, d->pose_b0, d->pose_w2, d->pose_b2, m->P))) return rc;
+  CCSP_CUDA_TRY(fetch(d->pose_w2, (size_t)CCSP_H * CCSP_HH, m->h_pose_w2));
 
   std::vector<float> h;
   CCSP_CUDA_TRY(fetch(d->dec_w0, (size_t)CCSP_HH * CCSP_H, h));
@@ -242,6 +246,11 @@ static int pack_tc_blobs(CcspModel *m, int math) {
   tc::pack_b_blob<M, 128>(m->h_dec_w1.data(), CCSP_H, 0, CCSP_H, CCSP_HH, b2.data());
   CCSP_CUDA_TRY(upload(m->pool, &m->blob_l1[math], b1));
   CCSP_CUDA_TRY(upload(m->pool, &m->blob_dec[math], b2));
+  if (M::KIND == tc::KIND_BF16) {
+    std::vector<uint8_t> b3((size_t)tc::NodeTcCfg<tc::Mode<tc::KIND_BF16, M::NSPLIT>>::NKC * M::NS * CCSP_H * tc::ROWB);
+    tc::pack_b_blob<M, CCSP_H>(m->h_pose_w2.data(), CCSP_HH, 0, CCSP_HH, CCSP_H, b3.data());
+    CCSP_CUDA_TRY(upload(m->pool, &m->blob_pose[math], b3));
+  }
   return CCSP_OK;
 }
 
@@ -373,6 +382,14 @@ static int launch_node(CcspPlan *p, const NodeArgs &a, cudaStream_t st) {
   if (!configured) {
     CCSP_CUDA_TRY(cudaFuncSetAttribute(k_node, cudaFuncAttributeMaxDynamicSharedMemorySize, NODE_SMEM_BYTES));
     configured = true;
+  }
+  // BF16 operand modes: the pose encoder's 128 -> 256 layer runs on tcgen05 (kernels_node_tc.cuh)
+  const int math = p->m->math;
+  if (edge_fused(math) && a.mode != NODE_EPS_OUT) {
+    if (math == CCSP_MATH_BF16X3) CCSP_CUDA_TRY((tc::launch_node_tc<tc::Mode<tc::KIND_BF16, 3>>(a, p->m->blob_pose[math], st)));
+    else CCSP_CUDA_TRY((tc::launch_node_tc<tc::Mode<tc::KIND_BF16, 1>>(a, p->m->blob_pose[math], st)));
+    count_launch();
+    return CCSP_OK;
   }
   unsigned blocks = (unsigned)((p->n + 1 + NODE_ROWS - 1) / NODE_ROWS);
   k_node<<<blocks, NODE_THREADS, NODE_SMEM_BYTES, st>>>(a);
