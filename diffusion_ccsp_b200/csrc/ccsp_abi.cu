@@ -3,6 +3,8 @@
 #include "../../include/ccsp_b200.h"
 
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -386,6 +388,27 @@ static int launch_node(CcspPlan *p, const NodeArgs &a, cudaStream_t st) {
   // BF16 operand modes: the pose encoder's 128 -> 256 layer runs on tcgen05 (kernels_node_tc.cuh)
   const int math = p->m->math;
   if (edge_fused(math) && a.mode != NODE_EPS_OUT) {
+    static const bool want_trace = getenv("CCSP_NODE_TRACE") != nullptr;
+    static long ncall = 0;
+    if (want_trace && ++ncall == 500) {      // developer aid: phase timeline of one launch (CTA 1: thread 0 and the MMA thread)
+      long long *d = nullptr, h[32];
+      CCSP_CUDA_TRY(cudaMalloc(&d, sizeof(h)));
+      CCSP_CUDA_TRY(cudaMemset(d, 0, sizeof(h)));
+      NodeArgs b = a;
+      b.trace = d;
+      CCSP_CUDA_TRY(cudaStreamSynchronize(st));
+      CCSP_CUDA_TRY((tc::launch_node_tc<tc::Mode<tc::KIND_BF16, 3>>(b, p->m->blob_pose[math], st)));
+      CCSP_CUDA_TRY(cudaStreamSynchronize(st));
+      CCSP_CUDA_TRY(cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost));
+      cudaFree(d);
+      fprintf(stderr, "[node trace] mode %d  t0:", a.mode);
+      for (int i = 0; i < 12; ++i) fprintf(stderr, " %lld", h[i] ? h[i] - h[0] : -1);
+      fprintf(stderr, "\n[node trace] mma thread:");
+      for (int i = 0; i < 12; ++i) fprintf(stderr, " %lld", h[16 + i] ? h[16 + i] - h[0] : -1);
+      fprintf(stderr, "\n");
+      count_launch();
+      return CCSP_OK;
+    }
     if (math == CCSP_MATH_BF16X3) CCSP_CUDA_TRY((tc::launch_node_tc<tc::Mode<tc::KIND_BF16, 3>>(a, p->m->blob_pose[math], st)));
     else CCSP_CUDA_TRY((tc::launch_node_tc<tc::Mode<tc::KIND_BF16, 1>>(a, p->m->blob_pose[math], st)));
     count_launch();

@@ -32,6 +32,15 @@
 namespace ccsp {
 namespace tc {
 
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------------
+// The sampling loop is a strict chain node -> edge -> node -> ...; with the launch attribute
+// cudaLaunchAttributeProgrammaticStreamSerialization the next kernel's CTAs become resident as soon as SMs free up
+// and run their prologue (barrier init, TMEM allocation, weight prefetch) under the tail of the previous kernel.
+// pdl_wait() blocks until the previous grid has completed and its writes are visible; every thread calls it before
+// its first access to data the previous kernel produced (or still reads).
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---- cluster / CTA-pair PTX wrappers ---------------------------------------------------------------
 __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
   uint32_t r;
@@ -179,6 +188,8 @@ struct Fused2Cfg {
   static constexpr int WARP_PROD0 = NUM_EPI, NUM_PROD_WARPS = 4;
   static constexpr int WARP_LOAD = 20, WARP_MMA1 = 21, WARP_MMA2 = 22, WARP_LOADW = 23;
   static constexpr int THREADS = 24 * 32;                     // 768
+  // the pool is what the CTA was launched with (768 x 80): 512 x 104 + 256 x 32 = 61 440 exactly
+  static constexpr int EPI_REGS = 104, AUX_REGS = 32;
   // barriers 512 | tb_s 2x256 | bd1 128 | w2t 128x8 | bd2 16 | red 3x128 float4
   static constexpr int SMEM_EXTRA = 512 + (512 + CCSP_HH + CCSP_MAXP * CCSP_HH + 16) * 4 + 3 * SUB_M * 16;
   static constexpr int SMEM_BYTES = OFF_EXTRA + SMEM_EXTRA + 1024;
@@ -220,6 +231,7 @@ __global__ void __launch_bounds__(Fused2Cfg<M>::THREADS, 1) k_edge_fused2_tc(con
 #define TR(role, slot) do { if (tr && it < 8) tr[((role) * 8 + it) * 16 + (slot)] = clock64(); } while (0)
 #define TRP(role, slot) do { if (tr && itp < 8) tr[((role) * 8 + itp) * 16 + (slot)] = clock64(); } while (0)
 
+  if (threadIdx.x == 0) pdl_launch_dependents();
   if (threadIdx.x == 0) {
     // ring 1: own gather threads + own weight loader (+ at the leader: the peer's relay lane)
     for (int s = 0; s < C::NSTAGE1; ++s) { mbar_init(&full1[s], C::NUM_PROD_WARPS * 32 + 1 + (leader ? 1 : 0)); mbar_init(&empty1[s], 1); }
@@ -244,7 +256,14 @@ __global__ void __launch_bounds__(Fused2Cfg<M>::THREADS, 1) k_edge_fused2_tc(con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
+  // Register re-partition (warpgroup-granular): the 16 epilogue warps take 104 registers so that a thread can hold
+  // its whole share of D1 (64 values) and release the accumulator right after two TMEM loads; the copy / issue /
+  // relay warps need few.
+#define REG_DEC() asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(C::AUX_REGS))
+#define REG_INC() asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(C::EPI_REGS))
+
   if (warp >= C::WARP_PROD0 && warp < C::WARP_PROD0 + C::NUM_PROD_WARPS) {
+    REG_DEC();
     // ============ A gather: this CTA's 128 edges; thread = (piece q, rows r0 + 32 p) ==================
     const int t = threadIdx.x - C::WARP_PROD0 * 32;
     const int q = t & 3, r0 = t >> 2;
@@ -252,6 +271,7 @@ __global__ void __launch_bounds__(Fused2Cfg<M>::THREADS, 1) k_edge_fused2_tc(con
     // when all its earlier cp.async have landed), so a thread never waits for data and all NSTAGE1 stages can be
     // in flight; the peer's barrier is forwarded to the leader by the relay lane below.
     uint32_t g = 0, it = 0;
+    pdl_wait();                          // pe_split is written by the preceding node kernel
     for (int u = unit0; u < num_units; u += unit_step, ++it) {
       const int m0 = ((u >> 1) * 2 + (int)rank) * SUB_M;
       size_t roff[4];
@@ -280,7 +300,9 @@ __global__ void __launch_bounds__(Fused2Cfg<M>::THREADS, 1) k_edge_fused2_tc(con
         if (t == 0) TR(7, kc);
       }
     }
-  } else if (warp == C::WARP_LOAD) {
+  } else if (warp >= C::WARP_LOAD) {
+    REG_DEC();       // one instruction for the whole warpgroup (warps 20-23), then the per-warp roles
+    if (warp == C::WARP_LOAD) {
     if (lane == 0) {
       // ============ first-layer weights: this CTA's 128 of the 256 rows of every chunk =================
       uint32_t g = 0;
@@ -409,7 +431,9 @@ __global__ void __launch_bounds__(Fused2Cfg<M>::THREADS, 1) k_edge_fused2_tc(con
         }
       }
     }
+  }
   } else if (warp < C::NUM_EPI) {
+    REG_INC();
     // ============ epilogues: warp w <-> TMEM lanes 32 (w & 3).., column group cg = w >> 2 =================
     const int quarter = warp & 3, cg = warp >> 2;
     const int r = quarter * 32 + lane;
@@ -419,6 +443,7 @@ __global__ void __launch_bounds__(Fused2Cfg<M>::THREADS, 1) k_edge_fused2_tc(con
     const uint32_t r_a2_full = mapa_u32(smem_u32(&a2_full[cg]), 0);
     // ---- epilogue-2 of unit itp (deferred by one unit: GEMM2 had a whole GEMM1 to finish): D2 -> o -------
     auto epi2 = [&](uint32_t itp, size_t rowp, int slotp) {
+      if (itp == 0) pdl_wait();          // o is still being read by the preceding node kernel until it completes
       const int trole = warp == 0 ? 2 : 3;
       const bool tron = lane == 0 && (warp == 0 || warp == 12);
       const uint32_t buf = itp & 1;
@@ -521,15 +546,15 @@ __global__ void __launch_bounds__(Fused2Cfg<M>::THREADS, 1) k_edge_fused2_tc(con
       if (tron) TR(trole, 2);
       tc_fence_after();
       const uint32_t taddr1 = tmem_base + cg * 64 + ((uint32_t)(quarter * 32) << 16);
+      float vall[64];
+      tmem_ld32(taddr1, vall);
+      tmem_ld32(taddr1 + 32, vall + 32);
+      tc_fence_before();                             // D1 fully in registers: GEMM1 of the next unit may overwrite it
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(r_tempty1);
 #pragma unroll
       for (int half = 0; half < 2; ++half) {         // 32 columns = one decoder k-chunk
-        float v[32];
-        tmem_ld32(taddr1 + half * 32, v);
-        if (half == 1) {                             // D1 fully in registers: GEMM1 of the next unit may overwrite it
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_remote(r_tempty1);
-        }
+        const float *v = vall + half * 32;
         if (tron) TR(trole, 3 + 2 * half);
 #pragma unroll
         for (int pc = 0; pc < 4; ++pc) {             // 8 columns -> one 16-byte piece of hi and of lo
@@ -567,6 +592,8 @@ __global__ void __launch_bounds__(Fused2Cfg<M>::THREADS, 1) k_edge_fused2_tc(con
   }
 #undef TR
 #undef TRP
+#undef REG_DEC
+#undef REG_INC
   tc_fence_before();
   __syncthreads();
   cluster_sync();                      // no CTA exits (or frees TMEM) while its peer may still signal it or read its operands
@@ -596,10 +623,12 @@ cudaError_t launch_fused2_tc(const FusedArgs &a, int num_sms, cudaStream_t st) {
   const int nclusters = units < max_clusters ? units : max_clusters;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(nclusters * 2); cfg.blockDim = dim3(C::THREADS); cfg.dynamicSmemBytes = C::SMEM_BYTES; cfg.stream = st;
-  cudaLaunchAttribute attrs[1];
+  cudaLaunchAttribute attrs[2];
   attrs[0].id = cudaLaunchAttributeClusterDimension;
   attrs[0].val.clusterDim.x = 2; attrs[0].val.clusterDim.y = 1; attrs[0].val.clusterDim.z = 1;
-  cfg.attrs = attrs; cfg.numAttrs = 1;
+  attrs[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attrs[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attrs; cfg.numAttrs = 2;
   return cudaLaunchKernelEx(&cfg, k_edge_fused2_tc<M>, a);
 }
 

@@ -153,6 +153,7 @@ struct NodeArgs {
   const float *W0, *b0, *W2t, *b2;   // pose encoder
   int pe_fmt;                    // 0: FP32 [n+1,256]; 1: TF32 split, 2: BF16 split  ([n+1][256 hi | 256 lo], kernels_tc.cuh)
   void *pe;
+  long long *trace;              // developer aid (CCSP_NODE_TRACE=1): clock64 at the phase boundaries of CTA 0, else nullptr
 };
 
 // 64 nodes per block, 512 threads.  Stage 0: one (node, component) pair per thread; stage 1: layer 1 of the

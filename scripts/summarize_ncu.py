@@ -36,7 +36,7 @@ def main(rep, prefix):
             names.append(n)
     with open(prefix + '_hotlines.txt', 'w') as f:
         for n in names:
-            short = n.split('(')[0].split('<')[0].split('::')[-1]
+            short = n.split('(')[0].split('<')[0].split('::')[-1].split()[-1]
             out = run(['-i', rep, '--page', 'source', '--print-source', 'cuda,sass', '--csv', '--kernel-name', 'regex:' + short,
                        '--launch-count', '1'])
             cur, lines = None, []
