@@ -17,6 +17,12 @@ from __future__ import annotations
 import argparse
 import json
 import os
+import sys as _sys
+
+if '--impl' in _sys.argv and 'reference' in _sys.argv:
+    # the CPU arm uses every host core; torchrun exports OMP_NUM_THREADS=1, which would pin numpy's BLAS to one thread
+    for _k in ('OMP_NUM_THREADS', 'OPENBLAS_NUM_THREADS', 'MKL_NUM_THREADS'):
+        os.environ[_k] = str(os.cpu_count() or 1)
 import statistics
 import subprocess
 import sys
@@ -54,6 +60,18 @@ def algorithmic_flops(E, n, P):
     dec = E * 2 * (2 * 256 * 128 + 2 * 128 * P)
     enc = n * (2 * P * 128 + 2 * 128 * 256)
     return dict(l1=l1, dec=dec, enc=enc, total=l1 + dec + enc)
+
+
+def ncu_traffic(kernel_key):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu --set full
+    capture (profiles/ncu_traffic.json, written by scripts/summarize_ncu.py); None when no capture is committed."""
+    p = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
+    if not os.path.exists(p):
+        return None
+    try:
+        return json.load(open(p)).get(kernel_key)
+    except Exception:
+        return None
 
 
 def peaks():
@@ -263,26 +281,41 @@ def run_ours(args):
                                    batch.mask.pin_memory())
         host_out = torch.empty((n, P), dtype=torch.float32).pin_memory()
 
+        e2e_parts = dict(plan_ms=0.0, sample_ms=0.0, d2h_ms=0.0)
+
         def e2e_step(i):
+            ta = time.perf_counter()
             den.drop_plans()
-            res = gd.sample(pinned, seed=5000 + i, node_offset=rank * n)
+            pl = den.plan_for(pinned)                                    # host batch -> HBM-resident plan (H2D inside)
+            tb_ = time.perf_counter()
+            res = gd.sample(pinned, seed=5000 + i, node_offset=rank * n)  # synchronises (reference bookkeeping)
+            tc_ = time.perf_counter()
             host_out.copy_(res, non_blocking=False)
-            return den.plan_for(pinned).h2d_bytes
+            td = time.perf_counter()
+            e2e_parts['plan_ms'] += (tb_ - ta) * 1e3; e2e_parts['sample_ms'] += (tc_ - tb_) * 1e3; e2e_parts['d2h_ms'] += (td - tc_) * 1e3
+            return pl.h2d_bytes
 
         e2e_step(0)
+        for k in e2e_parts:
+            e2e_parts[k] = 0.0
         barrier()
+        clk2 = ClockSampler(uuid if uuid.startswith('GPU-') else 'GPU-' + uuid)
+        clk2.start()
         t0 = time.perf_counter()
         nsteps = max(1, min(args.steps, 3))
         for i in range(nsteps):
             h2d = e2e_step(1 + i)
         barrier()
         dt = (time.perf_counter() - t0) / nsteps
+        clocks2 = clk2.stop()
         if world > 1:
             t = torch.tensor([dt], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
         e2e = dict(value=world * B / dt, unit='scenes/s', h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(n * P * 4),
-                   ms_per_step=dt * 1e3, api='GaussianDiffusion.sample(batch) with host batch; plan rebuilt every step')
+                   ms_per_step=dt * 1e3, steps=nsteps, clocks=clocks2,
+                   breakdown_ms={k: v / nsteps for k, v in e2e_parts.items()},
+                   api='GaussianDiffusion.sample(batch) with host batch; plan rebuilt every step')
 
     if rank == 0:
         pk = peaks()
@@ -294,7 +327,8 @@ def run_ours(args):
         achieved = dom_flops / (l1_ms * 1e-3) / 1e12 if l1_ms > 0 else None
         roofline = dict(bound='tensor', kernel='k_edge (first layer' + (' + decoder, fused)' if fused else ')'),
                         achieved=achieved, peak=pk['bf16_sustained'], unit='TFLOP/s',
-                        frac=(achieved / pk['bf16_sustained']) if achieved else None, traffic=None,
+                        frac=(achieved / pk['bf16_sustained']) if achieved else None,
+                        traffic=ncu_traffic('k_edge_fused2_tc' if fused else 'k_edge_l1_tc'),
                         peak_source=pk['source'] + ': bf16_tflops_sustained (kernel timed inside a long step)',
                         algorithmic_flops_per_launch=dom_flops, avg_launch_ms=l1_ms, launches_sampled=tm['samples'],
                         note=('FP32 FMA validation path: tensor-core fraction is expected to be tiny' if math == 'fp32' else

@@ -34,23 +34,62 @@ using namespace ccsp;
 
 namespace {
 
+// Device blocks of destroyed plans, kept by the model for the next plan: rebuilding a plan per batch (the end-to-end
+// path) would otherwise pay cudaFree/cudaMalloc of ~0.5 GB every time, and cudaFree of large blocks was measured at
+// 200-450 ms on the B200 boxes (scripts/plan_probe.py).
+struct BlockCache {
+  std::vector<std::pair<void *, size_t>> blocks;
+  size_t bytes = 0;
+  static constexpr size_t kCap = (size_t)8 << 30;
+  void *take(size_t need) {
+    int best = -1;
+    for (int i = 0; i < (int)blocks.size(); ++i)
+      if (blocks[i].second >= need && blocks[i].second <= 2 * need + ((size_t)1 << 20) &&
+          (best < 0 || blocks[i].second < blocks[best].second))
+        best = i;
+    if (best < 0) return nullptr;
+    void *p = blocks[best].first;
+    bytes -= blocks[best].second;
+    blocks.erase(blocks.begin() + best);
+    return p;
+  }
+  void give(void *p, size_t sz) {
+    if (bytes + sz > kCap) { cudaFree(p); return; }
+    blocks.emplace_back(p, sz);
+    bytes += sz;
+  }
+  void clear() {
+    for (auto &b : blocks) cudaFree(b.first);
+    blocks.clear();
+    bytes = 0;
+  }
+};
+
 struct DevPool {   // owns device allocations of a model / plan
-  std::vector<void *> ptrs;
+  std::vector<std::pair<void *, size_t>> ptrs;
+  BlockCache *cache = nullptr;    // plans: the owning model's cache
   template <typename T>
   cudaError_t alloc(T **out, size_t count) {
-    void *p = nullptr;
-    cudaError_t e = cudaMalloc(&p, (count ? count : 1) * sizeof(T));
-    if (e == cudaSuccess) ptrs.push_back(p);
+    size_t bytes = ((count ? count : 1) * sizeof(T) + 255) & ~(size_t)255;
+    void *p = cache ? cache->take(bytes) : nullptr;
+    cudaError_t e = cudaSuccess;
+    if (!p) e = cudaMalloc(&p, bytes);
+    if (e == cudaSuccess) ptrs.emplace_back(p, bytes);
     *out = (T *)p;
     return e;
   }
+  void drop(std::pair<void *, size_t> &q) {
+    if (!q.first) return;
+    if (cache) cache->give(q.first, q.second);
+    else cudaFree(q.first);
+    q.first = nullptr;
+  }
   void release(void *p) {
     for (auto &q : ptrs)
-      if (q == p) { cudaFree(q); q = nullptr; }
+      if (q.first == p) drop(q);
   }
   void free_all() {
-    for (void *p : ptrs)
-      if (p) cudaFree(p);
+    for (auto &q : ptrs) drop(q);
     ptrs.clear();
   }
 };
@@ -87,6 +126,7 @@ struct Encoder {
 
 }  // namespace
 
+struct CcspPlan;
 struct CcspModel {
   int device = 0;
   int G = 0, P = 0, Gr = 0, C = 0, normalize = 1, math = CCSP_MATH_FP32;
@@ -107,6 +147,8 @@ struct CcspModel {
   std::vector<float> h_dec_w1;    // [128][256]
   std::vector<float> h_pose_w2;   // [256][128] pose_encoder.2.weight (B operand of the tcgen05 node kernel)
   uint8_t *blob_pose[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  BlockCache cache;               // device blocks handed back by destroyed plans
+  std::vector<CcspPlan *> plans;  // live plans (detached from the cache if the model is destroyed first)
   uint8_t *blob_l1[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   uint8_t *blob_dec[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
 };
@@ -451,6 +493,8 @@ int ccsp_model_create(const CcspModelDesc *d, CcspModel **out) {
 
 void ccsp_model_destroy(CcspModel *m) {
   if (!m) return;
+  for (CcspPlan *p : m->plans) { p->pool.cache = nullptr; p->m = nullptr; }   // plans destroyed later free their own blocks
+  m->cache.clear();
   m->pool.free_all();
   delete m;
 }
@@ -541,6 +585,7 @@ int ccsp_plan_create(CcspModel *m, const float *x, int64_t n, int32_t F, const i
   // ---- device: upload + static term --------------------------------------------------------------
   g_upload_bytes = 0;
   CcspPlan *p = new CcspPlan();
+  p->pool.cache = &m->cache;
   p->m = m; p->n = n; p->E = E; p->Epad = Epad; p->num_tiles = (int)tile_type.size();
   auto fail = [&](int rc) { p->pool.free_all(); delete p; return rc; };
 #define PLAN_TRY(expr)                                                                             \
@@ -603,12 +648,19 @@ int ccsp_plan_create(CcspModel *m, const float *x, int64_t n, int32_t F, const i
   }
 #undef PLAN_TRY
   p->h2d_bytes = g_upload_bytes;
+  m->plans.push_back(p);
   *out = p;
   return CCSP_OK;
 }
 
 void ccsp_plan_destroy(CcspPlan *p) {
   if (!p) return;
+  cudaDeviceSynchronize();        // the blocks go back to the model's cache and may be reused at once
+  if (p->m) {
+    auto &v = p->m->plans;
+    for (size_t i = 0; i < v.size(); ++i)
+      if (v[i] == p) { v.erase(v.begin() + i); break; }
+  }
   for (cudaEvent_t e : p->ev) cudaEventDestroy(e);
   p->pool.free_all();
   delete p;

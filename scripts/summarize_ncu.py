@@ -29,6 +29,19 @@ def main(rep, prefix):
         w.writerow([h[i] for i in idx]); w.writerow([rows[1][i] for i in idx])
         for r in rows[2:]:
             w.writerow([r[i] for i in idx])
+    # per-kernel DRAM traffic (bytes per launch, mean over the captured launches) for bench.py's roofline.traffic
+    import json, os, collections
+    tr = collections.defaultdict(list)
+    ni, ri, wi = h.index('Kernel Name'), h.index('dram__bytes_read.sum'), h.index('dram__bytes_write.sum')
+    scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+    for r in rows[2:]:
+        short = r[ni].split('(')[0].split('<')[0].split('::')[-1].split()[-1]
+        tr[short].append(float(r[ri]) * scale[rows[1][ri]] + float(r[wi]) * scale[rows[1][wi]])
+    tj = os.path.join(os.path.dirname(prefix), 'ncu_traffic.json')
+    old = json.load(open(tj)) if os.path.exists(tj) else {}
+    old.update({k: sum(v) / len(v) for k, v in tr.items()})
+    old['_source'] = os.path.basename(prefix) + '_metrics.csv (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)'
+    json.dump(old, open(tj, 'w'), indent=1)
     names = []
     for r in rows[2:]:
         n = r[h.index('Kernel Name')]
