@@ -444,7 +444,7 @@ static int launch_node(CcspPlan *p, const NodeArgs &a, cudaStream_t st) {
       CCSP_CUDA_TRY(cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost));
       cudaFree(d);
       fprintf(stderr, "[node trace] mode %d  t0:", a.mode);
-      for (int i = 0; i < 12; ++i) fprintf(stderr, " %lld", h[i] ? h[i] - h[0] : -1);
+      for (int i = 0; i < 16; ++i) fprintf(stderr, " %lld", h[i] ? h[i] - h[0] : -1);
       fprintf(stderr, "\n[node trace] mma thread:");
       for (int i = 0; i < 12; ++i) fprintf(stderr, " %lld", h[16 + i] ? h[16 + i] - h[0] : -1);
       fprintf(stderr, "\n");

@@ -61,7 +61,9 @@ struct Philox4 { uint32_t x, y, z, w; };
 __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                                                  uint32_t k0, uint32_t k1) {
   const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
-#pragma unroll
+  // rolled on purpose: the callers are latency-bound kernels that run this once per launch from a cold instruction
+  // cache, where code size is time
+#pragma unroll 1
   for (int r = 0; r < 10; ++r) {
     uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
     uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;

@@ -33,15 +33,21 @@ struct NodeTcCfg {
   static constexpr int OFF_EXTRA = OFF_B + NKC * B_STAGE;
   static constexpr int ROW_THREADS = 512, THREADS = ROW_THREADS + 32;
   static constexpr int PARTS = ROW_THREADS / ROWS;            // 8 threads per node
-  static constexpr int STAGE_ENTRIES = 32;                    // incident (edge, endpoint) rows staged per node (rest: fallback)
-  static_assert(ROWS * STAGE_ENTRIES * 32 <= NKC * M::A_STAGE || M::NS == 1, "scratch must fit in the A operand region");
-  // barriers 64 | xs [64][8] | w0 [128][8] | b0 [128] | b2 [256]
-  static constexpr int SMEM_EXTRA = 64 + (ROWS * CCSP_MAXP + CCSP_HH * CCSP_MAXP + CCSP_HH + CCSP_H) * 4;
+  static constexpr int STAGE_ENTRIES = 31;                    // incident (edge, endpoint) rows staged per node (rest: fallback)
+  static constexpr int EW = M::NS == 2 ? 8 : 4;               // floats per staged entry (the NS == 1 A region is half as big)
+  // floats per node row of the scratch; = 28 (mod 32), so the 32 lanes (= 32 nodes) of a warp hit distinct banks
+  static constexpr int ROW_STRIDE = STAGE_ENTRIES * EW + (EW == 8 ? 4 : 0);
+  static_assert(ROW_STRIDE % 32 == 28 && ROWS * ROW_STRIDE * 4 <= NKC * M::A_STAGE, "scratch layout");
+  // barriers 64 | xs [64][8] | zs [64][8] | w0 [128][8] | b0 [128] | b2 [256]
+  static constexpr int SMEM_EXTRA = 64 + (2 * ROWS * CCSP_MAXP + CCSP_HH * CCSP_MAXP + CCSP_HH + CCSP_H) * 4;
   static constexpr int SMEM_BYTES = OFF_EXTRA + SMEM_EXTRA + 1024;
   static_assert(SMEM_BYTES <= 227 * 1024, "node kernel does not fit in shared memory");
 };
 
-template <class M>
+// PT: pose width known at compile time (2 boxes, 4 qualitative / triangles, 5 robot; 0 = read A.P at run time).  The
+// kernel runs once per launch from a cold instruction cache with two warps on its critical path, so the code it
+// has to fetch is its run time: a compile-time P removes every `p < P` predicate and the dead component code.
+template <class M, int PT>
 __global__ void __launch_bounds__(NodeTcCfg<M>::THREADS, 1) k_node_tc(const NodeArgs A, const uint8_t *__restrict__ w2_blob) {
   using C = NodeTcCfg<M>;
   extern __shared__ uint8_t smem_raw[];
@@ -51,17 +57,18 @@ __global__ void __launch_bounds__(NodeTcCfg<M>::THREADS, 1) k_node_tc(const Node
   uint64_t *tfull = bfull + 1;                                // accumulator complete
   uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(tfull + 1);
   float (*xs)[CCSP_MAXP] = reinterpret_cast<float (*)[CCSP_MAXP]>(extra + 64);
-  float *w0s = reinterpret_cast<float *>(extra + 64) + C::ROWS * CCSP_MAXP;   // [128][8]
+  float (*zs)[CCSP_MAXP] = reinterpret_cast<float (*)[CCSP_MAXP]>(extra + 64 + C::ROWS * CCSP_MAXP * 4);   // noise per node
+  float *w0s = reinterpret_cast<float *>(extra + 64) + 2 * C::ROWS * CCSP_MAXP;   // [128][8]
   float *b0s = w0s + CCSP_HH * CCSP_MAXP;                                      // [128]
   float *b2s = b0s + CCSP_HH;                                                  // [256]
   // scratch for the scatter-reduce: [64 rows][32 entries][8 floats], aliases the (not yet written) A operand region;
   // the NS == 1 layout has only 32 KB there, so it stages 4 floats per entry (P <= 4) or falls back
   float *scratch = reinterpret_cast<float *>(smem);
-  constexpr int EW = M::NS == 2 ? 8 : 4;                      // floats per staged entry
+  constexpr int EW = C::EW;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row0 = blockIdx.x * C::ROWS;
-  const int P = A.P;
+  const int P = PT ? PT : A.P;
   const uint32_t smem_base = smem_u32(smem);
   long long *const tr = (A.trace && blockIdx.x == 1 && (tid == 0 || tid == C::ROW_THREADS)) ? A.trace + (tid == 0 ? 0 : 16) : nullptr;
 #define NTR(slot) do { if (tr) tr[slot] = clock64(); } while (0)
@@ -86,56 +93,76 @@ __global__ void __launch_bounds__(NodeTcCfg<M>::THREADS, 1) k_node_tc(const Node
     if (tid < CCSP_HH) b0s[tid] = __ldg(&A.b0[tid]);
     if (tid < CCSP_H) b2s[tid] = __ldg(&A.b2[tid]);
   }
-  pdl_wait();                            // o / x / pe are produced (or still read) by the preceding edge kernel
-
   const int r = tid & (C::ROWS - 1), part = tid >> 6;         // row threads: node row, 1 of 8 helpers of that row
   const int v = row0 + r;
+  if (tid < C::ROW_THREADS) {
+    if (part == 1 && v < A.n && !A.z &&
+        (A.mode == NODE_DDPM || A.mode == NODE_ULA || (A.mode == NODE_INIT && !A.has_xinit))) {
+      float zz[CCSP_MAXP];               // the node's Philox draw, computed off the summing thread's critical path
+#pragma unroll
+      for (int p = 0; p < CCSP_MAXP; ++p) zz[p] = 0.f;
+      philox_normals(A.seed, A.draw, A.node_offset + (unsigned long long)v, P, zz);
+#pragma unroll
+      for (int p = 0; p < CCSP_MAXP; ++p) zs[r][p] = zz[p];
+    }
+  }
+  // Everything below this line and above pdl_wait() reads only plan constants (graph structure, mask, pinned poses,
+  // injected noise), so it runs under the tail of the preceding edge kernel: after the wait one dependent load level
+  // (the decoder outputs o, and x) is left on the critical path instead of three.
   const bool reduce = tid < C::ROW_THREADS && v < A.n && A.mode != NODE_INIT && A.mode != NODE_ENCODE;
   int k0 = 0, k1 = 0;
   bool masked = false;
-  float x_old[CCSP_MAXP], z_in[CCSP_MAXP], aux[CCSP_MAXP], gtv[CCSP_MAXP];   // loaded early by the node's summing thread (part == 0)
+  float x_old[CCSP_MAXP], z_in[CCSP_MAXP], aux[CCSP_MAXP], gtv[CCSP_MAXP];   // state of the node's summing thread (part == 0)
 #pragma unroll
   for (int p = 0; p < CCSP_MAXP; ++p) { x_old[p] = 0.f; z_in[p] = 0.f; aux[p] = 0.f; gtv[p] = 0.f; }
-  // ---- phase 1a: the 8 threads of a node fetch its incident decoder outputs in parallel -------------------------
-  if (tid < C::ROW_THREADS) {
-    if (tid < C::ROWS && v < A.n && A.mode != NODE_ENCODE) {
+  int src[4] = {0, 0, 0, 0};
+  int cnt = 0;
+  if (tid < C::ROW_THREADS && v < A.n && A.mode != NODE_ENCODE) {
+    masked = A.mask[v] != 0;
+    if (tid < C::ROWS) {
       const size_t ix = (size_t)v * P;
-      masked = A.mask[v] != 0;
 #pragma unroll
       for (int p = 0; p < CCSP_MAXP; ++p) {
         if (p >= P) continue;
-        if (A.mode != NODE_INIT) x_old[p] = A.x[ix + p];
         if (A.z) z_in[p] = A.z[ix + p];
         if (masked) aux[p] = (A.mode != NODE_INIT) ? A.xtail[ix + p] : 0.f;   // eps of a masked row = x[:, -P:]
         if (masked && A.pin) gtv[p] = A.gt[ix + p];
       }
     }
-    if (reduce) {
-      masked = A.mask[v] != 0;
-      if (!masked && P <= EW) {
-        k0 = A.node_ptr[v]; k1 = A.node_ptr[v + 1];
-        const int kend = min(k1, k0 + C::STAGE_ENTRIES);
-        int src[4];
-        int cnt = 0;
+    if (reduce && !masked && P <= EW) {
+      k0 = A.node_ptr[v]; k1 = A.node_ptr[v + 1];
+      const int kend = min(k1, k0 + C::STAGE_ENTRIES);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int k = k0 + part + j * C::PARTS;
-          if (k < kend) { src[j] = A.node_src[k]; cnt = j + 1; }
-        }
-        float *dst = scratch + ((size_t)r * C::STAGE_ENTRIES + part) * EW;
-        if (P == 4) {
-          float4 a[4];
+      for (int j = 0; j < 4; ++j) {
+        const int k = k0 + part + j * C::PARTS;
+        if (k < kend) { src[j] = A.node_src[k]; cnt = j + 1; }
+      }
+    }
+  }
+  pdl_wait();                            // o / x / pe are produced (or still read) by the preceding edge kernel
+
+  // ---- phase 1a: the 8 threads of a node fetch its incident decoder outputs in parallel -------------------------
+  if (tid < C::ROW_THREADS) {
+    if (tid < C::ROWS && v < A.n && A.mode != NODE_ENCODE && A.mode != NODE_INIT) {
+      const size_t ix = (size_t)v * P;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) if (j < cnt) a[j] = reinterpret_cast<const float4 *>(A.o)[src[j]];
+      for (int p = 0; p < CCSP_MAXP; ++p)
+        if (p < P) x_old[p] = A.x[ix + p];
+    }
+    if (cnt > 0) {
+      float *dst = scratch + (size_t)r * C::ROW_STRIDE + part * EW;
+      if (P == 4) {
+        float4 a[4];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) if (j < cnt) *reinterpret_cast<float4 *>(dst + j * C::PARTS * EW) = a[j];
-        } else {
+        for (int j = 0; j < 4; ++j) if (j < cnt) a[j] = reinterpret_cast<const float4 *>(A.o)[src[j]];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) if (j < cnt) {
-            const float *orow = A.o + (size_t)src[j] * P;
+        for (int j = 0; j < 4; ++j) if (j < cnt) *reinterpret_cast<float4 *>(dst + j * C::PARTS * EW) = a[j];
+      } else {
 #pragma unroll
-            for (int p = 0; p < EW; ++p) if (p < P) dst[j * C::PARTS * EW + p] = orow[p];
-          }
+        for (int j = 0; j < 4; ++j) if (j < cnt) {
+          const float *orow = A.o + (size_t)src[j] * P;
+#pragma unroll
+          for (int p = 0; p < EW; ++p) if (p < P) dst[j * C::PARTS * EW + p] = orow[p];
         }
       }
     }
@@ -161,7 +188,10 @@ __global__ void __launch_bounds__(NodeTcCfg<M>::THREADS, 1) k_node_tc(const Node
 #pragma unroll
         for (int p = 0; p < CCSP_MAXP; ++p) zz[p] = z_in[p];
         const bool need_z = (A.mode == NODE_DDPM || A.mode == NODE_ULA || (A.mode == NODE_INIT && !A.has_xinit));
-        if (need_z && !A.z) philox_normals(A.seed, A.draw, A.node_offset + (unsigned long long)v, P, zz);
+        if (need_z && !A.z) {
+#pragma unroll
+          for (int p = 0; p < CCSP_MAXP; ++p) zz[p] = zs[r][p];
+        }
         float eps[CCSP_MAXP];
 #pragma unroll
         for (int p = 0; p < CCSP_MAXP; ++p) eps[p] = 0.f;
@@ -173,7 +203,18 @@ __global__ void __launch_bounds__(NodeTcCfg<M>::THREADS, 1) k_node_tc(const Node
             int k = k0;
             if (P <= EW) {
               const int kend = min(k1, k0 + C::STAGE_ENTRIES);
-              const float *srow = scratch + (size_t)r * C::STAGE_ENTRIES * EW;
+              const float *srow = scratch + (size_t)r * C::ROW_STRIDE;
+              if (P <= 4) {                // loads batched by 4, adds strictly in order
+                for (; k + 4 <= kend; k += 4, srow += 4 * EW) {
+                  const float4 a0 = *reinterpret_cast<const float4 *>(srow), a1 = *reinterpret_cast<const float4 *>(srow + EW);
+                  const float4 a2 = *reinterpret_cast<const float4 *>(srow + 2 * EW), a3 = *reinterpret_cast<const float4 *>(srow + 3 * EW);
+                  eps[0] = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(eps[0], a0.x), a1.x), a2.x), a3.x);
+                  eps[1] = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(eps[1], a0.y), a1.y), a2.y), a3.y);
+                  eps[2] = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(eps[2], a0.z), a1.z), a2.z), a3.z);
+                  eps[3] = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(eps[3], a0.w), a1.w), a2.w), a3.w);
+                }
+              }
+#pragma unroll 1
               for (; k < kend; ++k, srow += EW) {
                 if (EW == 8) {
                   const float4 a0 = *reinterpret_cast<const float4 *>(srow), a1 = *reinterpret_cast<const float4 *>(srow + 4);
@@ -187,16 +228,19 @@ __global__ void __launch_bounds__(NodeTcCfg<M>::THREADS, 1) k_node_tc(const Node
             } else {
               k0 = A.node_ptr[v]; k1 = A.node_ptr[v + 1]; k = k0;
             }
+#pragma unroll 1
             for (; k < k1; ++k) {            // entries beyond the staged window (high-degree nodes)
               const float *orow = A.o + (size_t)A.node_src[k] * P;
               _Pragma("unroll") for (int p = 0; p < CCSP_MAXP; ++p) if (p < P) eps[p] = __fadd_rn(eps[p], orow[p]);
             }
+            NTR(12);
             if (A.normalize) {
               const float sd = sqrtf((float)(k1 - k0));
               _Pragma("unroll") for (int p = 0; p < CCSP_MAXP; ++p) if (p < P) eps[p] = eps[p] / sd;
             }
           }
         }
+        NTR(13);
 #pragma unroll
         for (int p = 0; p < CCSP_MAXP; ++p) {
           if (p >= P) continue;
@@ -219,6 +263,7 @@ __global__ void __launch_bounds__(NodeTcCfg<M>::THREADS, 1) k_node_tc(const Node
         }
       }
     }
+    NTR(14);
 #pragma unroll
     for (int p = 0; p < CCSP_MAXP; ++p) xs[r][p] = xn[p];
   }
@@ -232,7 +277,7 @@ __global__ void __launch_bounds__(NodeTcCfg<M>::THREADS, 1) k_node_tc(const Node
 #pragma unroll
     for (int d = 0; d < CCSP_MAXP; ++d) xr[d] = xs[r][d];
     uint8_t *a_stage = smem + (part >> 1) * M::A_STAGE;
-#pragma unroll
+#pragma unroll 1                          // (rolled: this kernel runs from a cold instruction cache, code size is time)
     for (int qq = 0; qq < 2; ++qq) {
       const int q = (part & 1) * 2 + qq;
       float f[8];
@@ -279,46 +324,61 @@ __global__ void __launch_bounds__(NodeTcCfg<M>::THREADS, 1) k_node_tc(const Node
     NTR(7);
     tc_fence_after();
     const uint32_t taddr = tmem_base + cg * 64 + ((uint32_t)(quarter * 32) << 16);
-    uint8_t *prow = reinterpret_cast<uint8_t *>(A.pe) + (size_t)vv * M::PE_ROW_BYTES;
+    // results are staged row-major in shared memory (the A operand region is free now) and written out coalesced:
+    // a lane-per-row store of 16 B at a 1 KB stride costs one L1 pass per lane, 4096 of them per CTA
+    uint8_t *orow = smem + (size_t)rr * M::PE_ROW_BYTES;
+#pragma unroll 1                          // rolled, 16 columns per iteration (see phase 1c)
+    for (int c16 = 0; c16 < 4; ++c16) {
+      float vals[16];
+      tmem_ld16(taddr + c16 * 16, vals);
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      float vals[32];
-      tmem_ld32(taddr + half * 32, vals);
-      const int c0 = cg * 64 + half * 32;
-      uint4 hi[4], lo[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
+      for (int h8 = 0; h8 < 2; ++h8) {
+        const int c0 = cg * 64 + c16 * 16 + h8 * 8;
         float f[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          f[i] = silu_raw(vals[q * 8 + i] + b2s[c0 + q * 8 + i]);
+          f[i] = silu_raw(vals[h8 * 8 + i] + b2s[c0 + i]);
           if (vv == A.n) f[i] = 0.f;     // zero row read by padded edges
         }
-        split_pair(f[0], f[1], hi[q].x, lo[q].x); split_pair(f[2], f[3], hi[q].y, lo[q].y);
-        split_pair(f[4], f[5], hi[q].z, lo[q].z); split_pair(f[6], f[7], hi[q].w, lo[q].w);
-      }
-      if (vv <= A.n) {
-        uint8_t *dh = prow + c0 * 2;
-        stg256(dh, hi[0], hi[1]); stg256(dh + 32, hi[2], hi[3]);
-        stg256(dh + M::PE_LO_OFF, lo[0], lo[1]); stg256(dh + M::PE_LO_OFF + 32, lo[2], lo[3]);
+        uint4 hi, lo;
+        split_pair(f[0], f[1], hi.x, lo.x); split_pair(f[2], f[3], hi.y, lo.y);
+        split_pair(f[4], f[5], hi.z, lo.z); split_pair(f[6], f[7], hi.w, lo.w);
+        // 16-byte chunk c of the row lives at chunk (c + row) & 63: the 32 lanes (= 32 rows) hit distinct banks
+        const int ch = c0 >> 3;          // hi chunk index 0..31; lo = +32
+        *reinterpret_cast<uint4 *>(orow + (((ch + rr) & 63) << 4)) = hi;
+        *reinterpret_cast<uint4 *>(orow + (((ch + 32 + rr) & 63) << 4)) = lo;
       }
     }
   }
   NTR(8 + (tid == 0 ? 0 : 1));
   tc_fence_before();
   __syncthreads();
+  if (tid < C::ROW_THREADS) {
+    // ---- phase 4: 16 warps copy the 64 rows of pe_split out, one coalesced 512-byte store per warp and half row ----
+#pragma unroll 1
+    for (int i = 0; i < C::ROWS / 16; ++i) {
+      const int rr = warp * (C::ROWS / 16) + i, vv = row0 + rr;
+      if (vv > A.n) break;
+      const uint8_t *src = smem + (size_t)rr * M::PE_ROW_BYTES;
+      uint8_t *dst = reinterpret_cast<uint8_t *>(A.pe) + (size_t)vv * M::PE_ROW_BYTES;
+      const uint4 a0 = *reinterpret_cast<const uint4 *>(src + (((lane + rr) & 63) << 4));
+      const uint4 a1 = *reinterpret_cast<const uint4 *>(src + (((lane + 32 + rr) & 63) << 4));
+      *reinterpret_cast<uint4 *>(dst + (lane << 4)) = a0;
+      *reinterpret_cast<uint4 *>(dst + ((lane + 32) << 4)) = a1;
+    }
+  }
   NTR(10);
   if (warp == C::ROW_THREADS / 32) tmem_dealloc(tmem_base, 256);
   NTR(11);
 #undef NTR
 }
 
-template <class M>
-cudaError_t launch_node_tc(const NodeArgs &a, const uint8_t *w2_blob, cudaStream_t st) {
+template <class M, int PT>
+cudaError_t launch_node_tc_p(const NodeArgs &a, const uint8_t *w2_blob, cudaStream_t st) {
   using C = NodeTcCfg<M>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(k_node_tc<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(k_node_tc<M, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     configured = true;
   }
@@ -329,7 +389,17 @@ cudaError_t launch_node_tc(const NodeArgs &a, const uint8_t *w2_blob, cudaStream
   attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;      // see pdl_wait() in kernels_fused2.cuh
   attrs[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attrs; cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, k_node_tc<M>, a, w2_blob);
+  return cudaLaunchKernelEx(&cfg, k_node_tc<M, PT>, a, w2_blob);
+}
+
+template <class M>
+cudaError_t launch_node_tc(const NodeArgs &a, const uint8_t *w2_blob, cudaStream_t st) {
+  switch (a.P) {
+    case 2: return launch_node_tc_p<M, 2>(a, w2_blob, st);
+    case 4: return launch_node_tc_p<M, 4>(a, w2_blob, st);
+    case 5: return launch_node_tc_p<M, 5>(a, w2_blob, st);
+    default: return launch_node_tc_p<M, 0>(a, w2_blob, st);
+  }
 }
 
 }  // namespace tc
