@@ -305,3 +305,57 @@ def test_trained_regime_vs_reference_golden(T, math):
     tol = {'fp32': 2e-5, 'tf32x3': 2e-5, 'bf16x3': 5e-5}[math]
     assert err < tol, err
     assert rel_err(torch.stack(hist).cpu().numpy()[::int(z['history_every'])], z['history']) < tol
+
+
+# ---------------------------------------------------------------------------------------------------
+# BASELINE.json configs 3-5 at their full per-GPU batch sizes: size-independent properties
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('case', [('boxes', 'diffuse_pairwise', False, 12, 4096),       # config 3: 1 x B200, 319 488 edges
+                                  ('triangles', 'diffuse_pairwise', True, 10, 1024),    # config 4: 8192 scenes / 8 GPUs
+                                  ('robot_box', 'robot_box', False, 6, 256)])           # config 5: 2048 scenes / 8 GPUs
+def test_full_batch_sizes_properties(case):
+    """Pinned rows equal gt, results finite, identical seeds give identical bits, a sharded run (two halves with
+    node_offset) reproduces the unsharded one bit for bit, launch count = 1 + 2 per evaluation."""
+    from diffusion_ccsp_b200 import _abi
+    kind, mode, tri, n_obj, n_scenes = case
+    dims = synthetic.dims_for(mode, tri)
+    sd = synthetic.make_state_dict(dims, mode, seed=2)
+    batch = scenes.make_batch(kind, n_scenes, n_obj, seed=3)
+    T, K = 12, 10
+    m, gd = build(mode, dims, sd, T=T, K=K, math='bf16x3')
+    gd.sample(batch, seed=5)                                  # builds the model, tables and plan
+    _abi.reset_launch_count()
+    a = gd.sample(batch, seed=5)
+    assert _abi.launch_count() == 1 + 2 * T * (1 + K)
+    b = gd.sample(batch, seed=5)
+    assert torch.equal(a, b)
+    assert bool(torch.isfinite(a).all())
+    mk = batch.mask.bool()
+    gt = batch.x[:, dims[-1][1]:dims[-1][2]]
+    assert torch.equal(a.cpu()[mk], gt[mk])
+    half = n_scenes // 2
+    per = batch.num_nodes // n_scenes
+    lo, hi = batch.select_scenes(0, half), batch.select_scenes(half, n_scenes)
+    parts = [gd.sample(lo, seed=5, node_offset=0), gd.sample(hi, seed=5, node_offset=half * per)]
+    assert torch.equal(torch.cat(parts, 0), a)
+
+
+def test_plan_rebuild_reuses_device_blocks_correctly():
+    """Plans of different sizes built one after the other on one model (device blocks are recycled through the model's
+    cache) give the same bits as on a fresh model."""
+    mode, dims = 'qualitative', synthetic.DIMS['qualitative']
+    sd = synthetic.make_trained_state_dict()
+    big = scenes.qualitative_batch(96, 8, seed=1)
+    small = scenes.qualitative_batch(24, 8, seed=2)
+    mid = scenes.qualitative_batch(60, 8, seed=3)
+    m, gd = build(mode, dims, sd, T=6, K=3, math='bf16x3')
+    first = {}
+    for name, b in (('big', big), ('small', small), ('mid', mid)):
+        m.drop_plans()
+        first[name] = gd.sample(b, seed=9).clone()
+    for name, b in (('small', small), ('big', big), ('mid', mid), ('small', small)):
+        m.drop_plans()                                        # every plan is rebuilt from recycled blocks
+        assert torch.equal(gd.sample(b, seed=9), first[name]), name
+    m2, gd2 = build(mode, dims, sd, T=6, K=3, math='bf16x3')  # fresh model, no recycled blocks
+    for name, b in (('mid', mid), ('big', big), ('small', small)):
+        assert torch.equal(gd2.sample(b, seed=9), first[name]), name
