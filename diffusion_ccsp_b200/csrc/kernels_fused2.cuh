@@ -27,6 +27,8 @@
 //   warp  22     leader CTA: GEMM2 issuer.  peer CTA: relays the decoder-weight ring likewise
 //   warp  23     decoder weight loader (one lane)
 #pragma once
+#include <cuda.h>
+
 #include "kernels_tc.cuh"
 
 namespace ccsp {
@@ -40,6 +42,65 @@ namespace tc {
 // its first access to data the previous kernel produced (or still reads).
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// ---- TMA (tensor-map) copies in CTA-pair mode --------------------------------------------------------
+// With .cta_group::2 the completion may be signalled on the PEER CTA's barrier (given by its shared::cluster
+// address), which is what lets both CTAs of a pair feed the leader's "stage full" barrier without a relay.
+// 4 rows of a 2-D tensor, picked by index, land as 4 consecutive box-wide rows of the destination tile; the tensor map
+// carries the shared-memory swizzle (probed in csrc/tests/tma_gather_test.cu: box {cols, 1}, SWIZZLE_64B reproduces
+// sw64_off exactly).
+__device__ __forceinline__ void tma_gather4_pair(uint32_t dst, const CUtensorMap *map, int col, int r0, int r1, int r2, int r3,
+                                                 uint32_t bar_cluster_addr) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes.cta_group::2 "
+               "[%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+               ::"r"(dst), "l"(map), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(bar_cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_tile2d_pair(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar_cluster_addr) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.tile.mbarrier::complete_tx::bytes.cta_group::2 "
+               "[%0], [%1, {%2, %3}], [%4];"
+               ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar_cluster_addr) : "memory");
+}
+
+// host: 2-D row-major tensor map (cuTensorMapEncodeTiled fetched through the runtime, libcuda is not linked)
+inline cudaError_t make_tmap_2d(CUtensorMap *map, const void *base, uint64_t cols, uint64_t rows, uint64_t row_bytes,
+                                uint32_t box_cols, uint32_t box_rows, bool swizzle64) {
+  typedef CUresult (*EncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeTiled enc = nullptr;
+  if (!enc) {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr);
+    if (e != cudaSuccess) return e;
+    if (!fn) return cudaErrorNotSupported;
+    enc = (EncodeTiled)fn;
+  }
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstr[1] = {row_bytes};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
+// the three tensor maps of the TMA variant of the pair kernel
+struct PairMaps {
+  CUtensorMap pe;   // pe_split as [n+1 rows][512 BF16] (hi | lo), box {32, 1}, SWIZZLE_64B: gather4 source of the A operand
+  CUtensorMap w1;   // first-layer weight blob as rows of 64 B, box {32, 128}: this CTA's half of one operand part
+  CUtensorMap wd;   // decoder weight blob as rows of 64 B, box {32, 64}
+};
+template <class M>
+inline cudaError_t make_pair_maps(PairMaps *pm, const void *pe_split, int64_t n_rows, const void *b_blob, int num_types,
+                                  const void *w_blob) {
+  cudaError_t e = make_tmap_2d(&pm->pe, pe_split, 2 * CCSP_H, (uint64_t)n_rows, M::PE_ROW_BYTES, 32, 1, true);
+  if (e != cudaSuccess) return e;
+  e = make_tmap_2d(&pm->w1, b_blob, 32, (uint64_t)num_types * 2 * M::NKC1 * M::NS * 256, ROWB, 32, 128, false);
+  if (e != cudaSuccess) return e;
+  return make_tmap_2d(&pm->wd, w_blob, 32, (uint64_t)M::NKC2 * M::NS * 128, ROWB, 32, 64, false);
+}
 
 // ---- cluster / CTA-pair PTX wrappers ---------------------------------------------------------------
 __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
@@ -208,8 +269,11 @@ struct Fused2Cfg {
   static_assert(SMEM_BYTES <= 227 * 1024, "pair kernel does not fit in shared memory");
 };
 
-template <class M>
-__global__ void __launch_bounds__(Fused2Cfg<M>::THREADS, 1) k_edge_fused2_tc(const FusedArgs A) {
+// TMA = true: operands arrive through tensor maps (A by tile::gather4, weights as 2-D tiles) whose completion is
+// signalled on the leader's barriers directly; TMA = false: cp.async gather + cp.async.bulk + relay lanes.
+template <class M, bool TMA>
+__global__ void __launch_bounds__(Fused2Cfg<M>::THREADS, 1)
+k_edge_fused2_tc(const FusedArgs A, const __grid_constant__ PairMaps maps) {
   using C = Fused2Cfg<M>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -235,9 +299,8 @@ __global__ void __launch_bounds__(Fused2Cfg<M>::THREADS, 1) k_edge_fused2_tc(con
   const int num_units = (A.num_m_tiles / 2) * 2;             // (pair of 128-edge tiles, slot)
   const int unit0 = blockIdx.x >> 1, unit_step = gridDim.x >> 1;
   const uint32_t smem_base = smem_u32(smem);
-  // (Letting the peer's cp.async.bulk complete_tx on the leader's barrier directly traps on B200: the barrier of a
-  // non-tensor bulk copy has to live in the destination CTA.  Hence the relay lanes.)
-  constexpr bool direct = false;
+  // (Letting the peer's NON-tensor cp.async.bulk complete_tx on the leader's barrier traps on B200: its barrier has to
+  // live in the destination CTA.  Hence the relay lanes of the TMA = false variant.)
   long long *const tr = (A.trace && blockIdx.x == 0) ? A.trace : nullptr;
 #define TR(role, slot) do { if (tr && it < 8) tr[((role) * 8 + it) * 16 + (slot)] = clock64(); } while (0)
 #define TRP(role, slot) do { if (tr && itp < 8) tr[((role) * 8 + itp) * 16 + (slot)] = clock64(); } while (0)
@@ -245,9 +308,10 @@ __global__ void __launch_bounds__(Fused2Cfg<M>::THREADS, 1) k_edge_fused2_tc(con
   if (threadIdx.x == 0) pdl_launch_dependents();
   if (threadIdx.x == 0) {
     // ring 1: own gather threads + own weight loader (+ at the leader: the peer's relay lane)
-    for (int s = 0; s < C::NSTAGE1; ++s) { mbar_init(&full1[s], C::NUM_PROD_WARPS * 32 + 1 + (leader ? 1 : 0)); mbar_init(&empty1[s], 1); }
+    // (TMA variant: leader only, one arrive.expect_tx per loader lane of the pair: 2 x A + 2 x weights)
+    for (int s = 0; s < C::NSTAGE1; ++s) { mbar_init(&full1[s], TMA ? 4 : C::NUM_PROD_WARPS * 32 + 1 + (leader ? 1 : 0)); mbar_init(&empty1[s], 1); }
     for (int s = 0; s < C::NA2; ++s) { mbar_init(&a2_full[s], 8); mbar_init(&a2_empty[2 * s], 1); mbar_init(&a2_empty[2 * s + 1], 1); }
-    for (int s = 0; s < C::NW; ++s) { mbar_init(&w_full[s], leader ? 2 : 1); mbar_init(&w_empty[s], 1); }
+    for (int s = 0; s < C::NW; ++s) { mbar_init(&w_full[s], (TMA || leader) ? 2 : 1); mbar_init(&w_empty[s], 1); }
     mbar_init(tfull1, 1); mbar_init(tempty1, 2 * C::NUM_EPI);
     for (int b = 0; b < 2; ++b) { mbar_init(&tfull2[b], 1); mbar_init(&tempty2[b], 2 * C::NUM_EPI); }
     fence_barrier_init();
@@ -275,6 +339,33 @@ __global__ void __launch_bounds__(Fused2Cfg<M>::THREADS, 1) k_edge_fused2_tc(con
 
   if (warp >= C::WARP_PROD0 && warp < C::WARP_PROD0 + C::NUM_PROD_WARPS) {
     REG_DEC();
+    if (TMA) {
+      // ============ A by TMA gather4: one warp, lane l owns rows 4l .. 4l+3 of this CTA's tile ===========
+      if (warp == C::WARP_PROD0) {
+        uint32_t g = 0;
+        uint32_t rfull[C::NSTAGE1];
+#pragma unroll
+        for (int s = 0; s < C::NSTAGE1; ++s) rfull[s] = mapa_u32(smem_u32(&full1[s]), 0);
+        pdl_wait();                      // pe_split is written by the preceding node kernel
+        for (int u = unit0; u < num_units; u += unit_step) {
+          const int m0 = ((u >> 1) * 2 + (int)rank) * SUB_M;
+          int4 idx = make_int4(0, 0, 0, 0);
+#pragma unroll 1
+          for (int kc = 0; kc < M::NKC1; ++kc, ++g) {
+            if (kc == 0 || kc == M::NKC1 / 2)
+              idx = __ldg(reinterpret_cast<const int4 *>((kc == 0 ? A.src_i : A.src_j) + m0) + lane);
+            const uint32_t s = g % C::NSTAGE1;
+            mbar_wait(&empty1[s], ((g / C::NSTAGE1) & 1) ^ 1);
+            if (A.dbg & 1) { if (lane == 0) mbar_arrive_remote(rfull[s]); continue; }
+            if (lane == 0) mbar_arrive_expect_tx_remote(rfull[s], M::A_STAGE);
+            const uint32_t dst = smem_base + s * C::STAGE1 + lane * 4 * ROWB;
+            const int col = (kc % (M::NKC1 / 2)) * M::KC;
+            tma_gather4_pair(dst, &maps.pe, col, idx.x, idx.y, idx.z, idx.w, rfull[s]);
+            if (M::NS == 2) tma_gather4_pair(dst + PART, &maps.pe, CCSP_H + col, idx.x, idx.y, idx.z, idx.w, rfull[s]);
+          }
+        }
+      }
+    } else {
     // ============ A gather: this CTA's 128 edges; thread = (piece q, rows r0 + 32 p) ==================
     const int t = threadIdx.x - C::WARP_PROD0 * 32;
     const int q = t & 3, r0 = t >> 2;
@@ -311,6 +402,7 @@ __global__ void __launch_bounds__(Fused2Cfg<M>::THREADS, 1) k_edge_fused2_tc(con
         if (t == 0) TR(7, kc);
       }
     }
+    }
   } else if (warp >= C::WARP_LOAD) {
     REG_DEC();       // one instruction for the whole warpgroup (warps 20-23), then the per-warp roles
     if (warp == C::WARP_LOAD) {
@@ -324,11 +416,17 @@ __global__ void __launch_bounds__(Fused2Cfg<M>::THREADS, 1) k_edge_fused2_tc(con
         for (int kc = 0; kc < M::NKC1; ++kc, ++g) {
           const uint32_t s = g % C::NSTAGE1;
           mbar_wait(&empty1[s], ((g / C::NSTAGE1) & 1) ^ 1);
-          // direct mode: the copy's complete_tx lands on the LEADER's barrier; relay mode: on the local one
-          const uint32_t bar = direct ? mapa_u32(smem_u32(&full1[s]), 0) : smem_u32(&full1[s]);
+          // TMA variant: the copy's complete_tx lands on the LEADER's barrier; relay variant: on the local one
+          const uint32_t bar = TMA ? mapa_u32(smem_u32(&full1[s]), 0) : smem_u32(&full1[s]);
           if (A.dbg & 2) { mbar_arrive_remote(bar); continue; }
           mbar_arrive_expect_tx_remote(bar, C::B1_STAGE);
           const uint32_t dst = smem_base + s * C::STAGE1 + M::A_STAGE;
+          if (TMA) {
+            const int row = ((grp * 2 + slot) * M::NKC1 + kc) * (M::NS * C::NT1) + (int)rank * (C::NT1 / 2);
+            tma_tile2d_pair(dst, &maps.w1, 0, row, bar);
+            if (M::NS == 2) tma_tile2d_pair(dst + C::B1_PART, &maps.w1, 0, row + C::NT1, bar);
+            continue;
+          }
           const uint8_t *src = blob + (size_t)kc * C::B1_BLOB_STAGE;
           bulk_g2s_rbar(dst, src, C::B1_PART, bar);
           if (M::NS == 2) bulk_g2s_rbar(dst + C::B1_PART, src + C::B1_BLOB_PART, C::B1_PART, bar);
@@ -345,11 +443,17 @@ __global__ void __launch_bounds__(Fused2Cfg<M>::THREADS, 1) k_edge_fused2_tc(con
         for (int q = 0; q < 8; ++q, ++g2) {
           const uint32_t s = g2 % C::NW;
           mbar_wait(&w_empty[s], ((g2 / C::NW) & 1) ^ 1);
-          const uint32_t bar = direct ? mapa_u32(smem_u32(&w_full[s]), 0) : smem_u32(&w_full[s]);
+          const uint32_t bar = TMA ? mapa_u32(smem_u32(&w_full[s]), 0) : smem_u32(&w_full[s]);
           if (A.dbg & 2) { mbar_arrive_remote(bar); continue; }
           const int c = 2 * (q & 3) + (q >> 2);
           mbar_arrive_expect_tx_remote(bar, C::W_STAGE);
           const uint32_t dst = smem_base + C::OFF_W + s * C::W_STAGE;
+          if (TMA) {
+            const int row = c * (M::NS * C::NT2) + (int)rank * (C::NT2 / 2);
+            tma_tile2d_pair(dst, &maps.wd, 0, row, bar);
+            if (M::NS == 2) tma_tile2d_pair(dst + C::W_PART, &maps.wd, 0, row + C::NT2, bar);
+            continue;
+          }
           const uint8_t *src = blob + (size_t)c * C::W_BLOB_STAGE;
           bulk_g2s_rbar(dst, src, C::W_PART, bar);
           if (M::NS == 2) bulk_g2s_rbar(dst + C::W_PART, src + C::W_BLOB_PART, C::W_PART, bar);
@@ -381,7 +485,7 @@ __global__ void __launch_bounds__(Fused2Cfg<M>::THREADS, 1) k_edge_fused2_tc(con
           umma_commit2(tfull1);
           TR(0, 4);
         }
-      } else {
+      } else if (!TMA) {
         // ============ peer: forward "stage s is full here (A rows + weight half)" to the leader ==========
         uint32_t g = 0;
         uint32_t rfull[C::NSTAGE1];
@@ -428,7 +532,7 @@ __global__ void __launch_bounds__(Fused2Cfg<M>::THREADS, 1) k_edge_fused2_tc(con
           umma_commit2(&tfull2[buf]);
           TR(1, 6);
         }
-      } else {
+      } else if (!TMA) {
         uint32_t g2 = 0;
         uint32_t rfull[C::NW];
 #pragma unroll
@@ -611,12 +715,12 @@ __global__ void __launch_bounds__(Fused2Cfg<M>::THREADS, 1) k_edge_fused2_tc(con
   if (warp == C::WARP_MMA1) tmem_dealloc2(tmem_base, 512);
 }
 
-template <class M>
-cudaError_t launch_fused2_tc(const FusedArgs &a, int num_sms, cudaStream_t st) {
+template <class M, bool TMA>
+cudaError_t launch_fused2_impl(const FusedArgs &a, const PairMaps &maps, int num_sms, cudaStream_t st) {
   using C = Fused2Cfg<M>;
   static int max_clusters = 0;
   if (max_clusters == 0) {
-    cudaError_t e = cudaFuncSetAttribute(k_edge_fused2_tc<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(k_edge_fused2_tc<M, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t q = {};
     q.gridDim = dim3(num_sms / 2 * 2); q.blockDim = dim3(C::THREADS); q.dynamicSmemBytes = C::SMEM_BYTES;
@@ -624,7 +728,7 @@ cudaError_t launch_fused2_tc(const FusedArgs &a, int num_sms, cudaStream_t st) {
     at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     q.attrs = at; q.numAttrs = 1;
     int n = 0;
-    e = cudaOccupancyMaxActiveClusters(&n, k_edge_fused2_tc<M>, &q);
+    e = cudaOccupancyMaxActiveClusters(&n, k_edge_fused2_tc<M, TMA>, &q);
     if (e != cudaSuccess) return e;
     max_clusters = (n > 0 && n < num_sms / 2) ? n : num_sms / 2;
   }
@@ -640,7 +744,15 @@ cudaError_t launch_fused2_tc(const FusedArgs &a, int num_sms, cudaStream_t st) {
   attrs[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attrs[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attrs; cfg.numAttrs = 2;
-  return cudaLaunchKernelEx(&cfg, k_edge_fused2_tc<M>, a);
+  return cudaLaunchKernelEx(&cfg, k_edge_fused2_tc<M, TMA>, a, maps);
+}
+
+// maps == nullptr selects the cp.async / relay variant
+template <class M>
+cudaError_t launch_fused2_tc(const FusedArgs &a, int num_sms, cudaStream_t st, const PairMaps *maps = nullptr) {
+  if (maps) return launch_fused2_impl<M, true>(a, *maps, num_sms, st);
+  static const PairMaps none = {};
+  return launch_fused2_impl<M, false>(a, none, num_sms, st);
 }
 
 }  // namespace tc

@@ -190,7 +190,7 @@ static void run_chain(const Problem &p, const std::vector<double> *Href, const s
 static int g_dbg_or = 0;
 static bool g_trace = false;   // OR'ed into the pair kernel's dbg word (256: relay mode)
 // fused kernels: o only (PAIR: CTA-pair / cta_group::2 version)
-template <class M, bool PAIR = false>
+template <class M, int PAIR = 0>   // 0: single-CTA fused prototype, 1: CTA pair (cp.async + relay), 2: CTA pair (TMA)
 static void run_fused(const Problem &p, const std::vector<double> *oref, int iters, int sms, Report &o, int dbg = 0) {
   const int rows = p.m_tiles * 128;
   std::vector<float> Sblk((size_t)rows * 512);
@@ -210,13 +210,20 @@ static void run_fused(const Problem &p, const std::vector<double> *oref, int ite
   memset(&a, 0, sizeof(a));
   a.pe_split = d_pe; a.src_i = d_i0; a.src_j = d_i1; a.b_blob = d_b1; a.w_blob = d_b2; a.tile_type = d_tt; a.num_m_tiles = p.m_tiles;
   a.S = d_S; a.tb = d_tb; a.bd1 = d_bd1; a.Wd2 = d_w2; a.bd2 = d_bd2; a.P = p.P; a.o = d_o; a.dbg = dbg | (PAIR ? g_dbg_or : 0);
+  PairMaps pm;
+  memset(&pm, 0, sizeof(pm));
+  if (PAIR == 2) CK((make_pair_maps<M>(&pm, d_pe, (int64_t)(pe.size() / M::PE_ROW_BYTES), d_b1, p.groups, d_b2)));
+  auto launch = [&]() -> cudaError_t {
+    if (PAIR == 0) return launch_fused_tc<M>(a, sms, 0);
+    return launch_fused2_tc<M>(a, sms, 0, PAIR == 2 ? &pm : nullptr);
+  };
   long long *d_tr = nullptr;
   if (PAIR && g_trace) {
     CK(cudaMalloc(&d_tr, 8 * 8 * 16 * sizeof(long long)));
     CK(cudaMemset(d_tr, 0, 8 * 8 * 16 * sizeof(long long)));
     a.trace = d_tr;
   }
-  CK((PAIR ? launch_fused2_tc<M>(a, sms, 0) : launch_fused_tc<M>(a, sms, 0)));
+  CK(launch());
   CK(cudaDeviceSynchronize());
   if (d_tr) {
     std::vector<long long> tr(8 * 8 * 16);
@@ -243,7 +250,7 @@ static void run_fused(const Problem &p, const std::vector<double> *oref, int ite
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     CK(cudaEventRecord(e0));
-    for (int i = 0; i < iters; ++i) CK((PAIR ? launch_fused2_tc<M>(a, sms, 0) : launch_fused_tc<M>(a, sms, 0)));
+    for (int i = 0; i < iters; ++i) CK(launch());
     CK(cudaEventRecord(e1));
     CK(cudaEventSynchronize(e1));
     float ms;
@@ -308,8 +315,10 @@ int main(int argc, char **argv) {
     run_fused<Mode<KIND_BF16, 3>>(p, &oref, 0, sms, o); chk("o fused bf16x3", o, 2e-5);
     run_fused<Mode<KIND_BF16, 1>>(p, &oref, 0, sms, o); chk("o fused bf16", o, 4e-2);
     }
-    run_fused<Mode<KIND_BF16, 3>, true>(p, &oref, 0, sms, o); chk("o pair bf16x3", o, 2e-5);
-    run_fused<Mode<KIND_BF16, 1>, true>(p, &oref, 0, sms, o); chk("o pair bf16", o, 4e-2);
+    run_fused<Mode<KIND_BF16, 3>, 1>(p, &oref, 0, sms, o); chk("o pair bf16x3", o, 2e-5);
+    run_fused<Mode<KIND_BF16, 1>, 1>(p, &oref, 0, sms, o); chk("o pair bf16", o, 4e-2);
+    run_fused<Mode<KIND_BF16, 3>, 2>(p, &oref, 0, sms, o); chk("o pairTMA bf16x3", o, 2e-5);
+    run_fused<Mode<KIND_BF16, 1>, 2>(p, &oref, 0, sms, o); chk("o pairTMA bf16", o, 4e-2);
   }
   if (perf && fails == 0) {
     // ---- throughput at the config-2 size: 632 edge tiles (80 896 rows), 13 weight groups ---------------
@@ -322,11 +331,17 @@ int main(int argc, char **argv) {
     if (pair_only) {
       Report f;
       const double ff = fl1 + fdec;
-      run_fused<Mode<KIND_BF16, 3>, true>(p, nullptr, 20, sms, f); printf("%-30s fused %.3f ms %6.1f TFLOP/s\n", "bf16x3 pair", f.ms, ff / f.ms / 1e9);
-      run_fused<Mode<KIND_BF16, 1>, true>(p, nullptr, 20, sms, f); printf("%-30s fused %.3f ms %6.1f TFLOP/s\n", "bf16 pair", f.ms, ff / f.ms / 1e9);
+      run_fused<Mode<KIND_BF16, 3>, 1>(p, nullptr, 20, sms, f); printf("%-30s fused %.3f ms %6.1f TFLOP/s\n", "bf16x3 pair", f.ms, ff / f.ms / 1e9);
+      run_fused<Mode<KIND_BF16, 1>, 1>(p, nullptr, 20, sms, f); printf("%-30s fused %.3f ms %6.1f TFLOP/s\n", "bf16 pair", f.ms, ff / f.ms / 1e9);
       for (int dbg : {1, 2, 4, 7, 8, 15}) {
-        run_fused<Mode<KIND_BF16, 3>, true>(p, nullptr, 10, sms, f, dbg);
+        run_fused<Mode<KIND_BF16, 3>, 1>(p, nullptr, 10, sms, f, dbg);
         printf("bf16x3 pair dbg=%-2d               fused %.3f ms %6.1f TFLOP/s\n", dbg, f.ms, ff / f.ms / 1e9);
+      }
+      run_fused<Mode<KIND_BF16, 3>, 2>(p, nullptr, 20, sms, f); printf("%-30s fused %.3f ms %6.1f TFLOP/s\n", "bf16x3 pair TMA", f.ms, ff / f.ms / 1e9);
+      run_fused<Mode<KIND_BF16, 1>, 2>(p, nullptr, 20, sms, f); printf("%-30s fused %.3f ms %6.1f TFLOP/s\n", "bf16 pair TMA", f.ms, ff / f.ms / 1e9);
+      for (int dbg : {1, 2, 4, 7, 8, 15}) {
+        run_fused<Mode<KIND_BF16, 3>, 2>(p, nullptr, 10, sms, f, dbg);
+        printf("bf16x3 pair TMA dbg=%-2d           fused %.3f ms %6.1f TFLOP/s\n", dbg, f.ms, ff / f.ms / 1e9);
       }
       printf(fails ? "RESULT: FAIL (%d)\n" : "RESULT: PASS\n", fails);
       return fails ? 1 : 0;
@@ -346,10 +361,10 @@ int main(int argc, char **argv) {
       const double ff = fl1 + fdec;
       run_fused<Mode<KIND_BF16, 3>>(p, nullptr, 20, sms, f); printf("%-30s fused %.3f ms %6.1f TFLOP/s\n", "bf16x3 fused", f.ms, ff / f.ms / 1e9);
       run_fused<Mode<KIND_BF16, 1>>(p, nullptr, 20, sms, f); printf("%-30s fused %.3f ms %6.1f TFLOP/s\n", "bf16 fused", f.ms, ff / f.ms / 1e9);
-      run_fused<Mode<KIND_BF16, 3>, true>(p, nullptr, 20, sms, f); printf("%-30s fused %.3f ms %6.1f TFLOP/s\n", "bf16x3 pair", f.ms, ff / f.ms / 1e9);
-      run_fused<Mode<KIND_BF16, 1>, true>(p, nullptr, 20, sms, f); printf("%-30s fused %.3f ms %6.1f TFLOP/s\n", "bf16 pair", f.ms, ff / f.ms / 1e9);
+      run_fused<Mode<KIND_BF16, 3>, 1>(p, nullptr, 20, sms, f); printf("%-30s fused %.3f ms %6.1f TFLOP/s\n", "bf16x3 pair", f.ms, ff / f.ms / 1e9);
+      run_fused<Mode<KIND_BF16, 1>, 1>(p, nullptr, 20, sms, f); printf("%-30s fused %.3f ms %6.1f TFLOP/s\n", "bf16 pair", f.ms, ff / f.ms / 1e9);
       for (int dbg : {1, 2, 4, 7, 8, 15}) {
-        run_fused<Mode<KIND_BF16, 3>, true>(p, nullptr, 10, sms, f, dbg);
+        run_fused<Mode<KIND_BF16, 3>, 1>(p, nullptr, 10, sms, f, dbg);
         printf("bf16x3 pair dbg=%-2d               fused %.3f ms %6.1f TFLOP/s\n", dbg, f.ms, ff / f.ms / 1e9);
       }
       for (int dbg : {1, 2, 4, 7, 8, 15}) {
