@@ -359,3 +359,26 @@ def test_plan_rebuild_reuses_device_blocks_correctly():
     m2, gd2 = build(mode, dims, sd, T=6, K=3, math='bf16x3')  # fresh model, no recycled blocks
     for name, b in (('mid', mid), ('big', big), ('small', small)):
         assert torch.equal(gd2.sample(b, seed=9), first[name]), name
+
+
+@pytest.mark.parametrize('math', EXACT_MATHS)
+@pytest.mark.parametrize('case', [('qualitative', False, 13, 6), ('diffuse_pairwise', False, 2, 4), ('robot_box', False, 2, 28)])
+def test_high_degree_nodes_trajectory_vs_oracle(case, math):
+    """Hub nodes with more incident (edge, endpoint) rows than the node kernel stages in shared memory (31): the
+    overflow path must keep the reference's accumulation order.  Short ULA trajectory with injected noise."""
+    mode, tri, n_types, F = case
+    dims = synthetic.dims_for(mode, tri)
+    P = dims[-1][0]
+    rng = np.random.default_rng(11)
+    sd = synthetic.make_state_dict(dims, mode, seed=3)
+    parts = [scenes.random_typed_scene(rng, n_obj, n_types, n_edges, F) for n_obj, n_edges in ((3, 150), (9, 40), (2, 90), (70, 200))]
+    batch = scenes.collate(parts)
+    deg = np.bincount(batch.edge_index.numpy().reshape(-1), minlength=batch.num_nodes)
+    assert deg.max() > 64 and deg.min() >= 1
+    T, K = 3, 2
+    _, gd = build(mode, dims, sd, T=T, K=K, math=math)
+    noise = synthetic.make_noise(T, K, batch.num_nodes, P, seed=21)
+    ref = orc.OracleDiffusion(orc.OracleDenoiser(np_sd(sd), dims, mode), T, 'ULA', K).p_sample_loop(batch, noise.numpy())
+    out = gd.sample(batch, noise=noise).cpu().numpy()
+    record(f'hub_{mode}_traj_T{T}_K{K}', math, rel_err(out, ref))
+    assert rel_err(out, ref) < TOL[math]['traj'], rel_err(out, ref)
