@@ -136,6 +136,15 @@ __device__ __forceinline__ bool mbar_try_wait_cl(uint64_t *bar, uint32_t parity)
       : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
   return ok != 0;
 }
+__device__ __forceinline__ bool mbar_test_wait(uint64_t *bar, uint32_t parity) {      // non-blocking
+  uint32_t ok;
+  asm volatile(
+      "{\n.reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n}"
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait_cl(uint64_t *bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait_cl(bar, parity)) {
@@ -470,17 +479,20 @@ k_edge_fused2_tc(const FusedArgs A, const __grid_constant__ PairMaps maps) {
           mbar_wait_cl(tempty1, (it & 1) ^ 1);
           TR(0, 1);
           tc_fence_after();
+          bool ready = false;              // the stage of this chunk was already seen full by the peek below
           for (int kc = 0; kc < M::NKC1; ++kc, ++g) {
             const uint32_t s = g % C::NSTAGE1;
-            mbar_wait_cl(&full1[s], (g / C::NSTAGE1) & 1);
+            if (!ready) mbar_wait_cl(&full1[s], (g / C::NSTAGE1) & 1);
             if (kc == 0) TR(0, 2);
             if (kc == 8) TR(0, 3);
-            TR(4, kc);
             tc_fence_after();
             const uint32_t a_hi = smem_base + s * C::STAGE1;
-            if (!(A.dbg & 8)) issue_chunk2<M, C::NT1>(tmem_base, a_hi, a_hi + M::A_STAGE, C::B1_PART, kc == 0);
+            if (!(A.dbg & 8)) issue_kstep2<M, C::NT1>(tmem_base, a_hi, a_hi + M::A_STAGE, C::B1_PART, 0, kc == 0);
+            // peek at the next stage while this chunk's MMAs are queued, so that its first MMA can follow the commit
+            // without the barrier round trip (non-blocking: a blocking wait here would delay this stage's release)
+            ready = kc + 1 < M::NKC1 && mbar_test_wait(&full1[(g + 1) % C::NSTAGE1], ((g + 1) / C::NSTAGE1) & 1);
+            if (!(A.dbg & 8)) issue_kstep2<M, C::NT1>(tmem_base, a_hi, a_hi + M::A_STAGE, C::B1_PART, 1, false);
             umma_commit2(&empty1[s]);
-            TR(5, kc);
           }
           umma_commit2(tfull1);
           TR(0, 4);
