@@ -422,7 +422,10 @@ static NodeArgs node_args_base(CcspPlan *p) {
 }
 
 static int launch_node(CcspPlan *p, const NodeArgs &a, cudaStream_t st) {
-  static bool configured = false;
+  static bool configured_dev[64] = {};      // per device: function attributes belong to the device's context
+  int dev_ = 0;
+  cudaGetDevice(&dev_);
+  bool &configured = configured_dev[dev_ & 63];
   if (!configured) {
     CCSP_CUDA_TRY(cudaFuncSetAttribute(k_node, cudaFuncAttributeMaxDynamicSharedMemorySize, NODE_SMEM_BYTES));
     configured = true;

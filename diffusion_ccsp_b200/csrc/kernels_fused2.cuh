@@ -730,7 +730,10 @@ k_edge_fused2_tc(const FusedArgs A, const __grid_constant__ PairMaps maps) {
 template <class M, bool TMA>
 cudaError_t launch_fused2_impl(const FusedArgs &a, const PairMaps &maps, int num_sms, cudaStream_t st) {
   using C = Fused2Cfg<M>;
-  static int max_clusters = 0;
+  static int max_clusters_dev[64] = {};      // per device: function attributes and cluster occupancy
+  int dev_ = 0;
+  cudaGetDevice(&dev_);
+  int &max_clusters = max_clusters_dev[dev_ & 63];
   if (max_clusters == 0) {
     cudaError_t e = cudaFuncSetAttribute(k_edge_fused2_tc<M, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) return e;

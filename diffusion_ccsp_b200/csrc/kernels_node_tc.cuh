@@ -376,7 +376,10 @@ __global__ void __launch_bounds__(NodeTcCfg<M>::THREADS, 1) k_node_tc(const Node
 template <class M, int PT>
 cudaError_t launch_node_tc_p(const NodeArgs &a, const uint8_t *w2_blob, cudaStream_t st) {
   using C = NodeTcCfg<M>;
-  static bool configured = false;
+  static bool configured_dev[64] = {};      // per device: function attributes belong to the device's context
+  int dev_ = 0;
+  cudaGetDevice(&dev_);
+  bool &configured = configured_dev[dev_ & 63];
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(k_node_tc<M, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) return e;

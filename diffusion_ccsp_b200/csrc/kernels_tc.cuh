@@ -692,13 +692,9 @@ __global__ void __launch_bounds__(DecCfg<M>::THREADS, 1) k_edge_dec_tc(const Dec
 }
 
 // ===================================================================================================
-// fused edge kernel (BF16 operand modes): first layer -> SiLU -> split -> decoder -> o, H never leaves the SM
+// arguments of the fused edge kernel (BF16 operand modes, kernels_fused2.cuh):
+// first layer -> SiLU -> split -> decoder -> o, H never leaves the SM
 // ===================================================================================================
-// Per (128-edge tile, slot):  GEMM1 D1[128x256] (TMEM cols 0..255)  ->  epilogue-1 turns D1 into decoder
-// operand chunks (32 K-columns each) written to a 2-stage shared-memory ring (one stage per epilogue column
-// group)  ->  GEMM2 D2[128x128] (TMEM cols 256..383) consumes them against streamed Wd1 chunks  ->  epilogue-2
-// (SiLU, 128->P, scatter rows of o).  D1 is single-buffered (TMEM: 256 + 128 of 512 columns), so GEMM1 of the
-// next tile starts as soon as epilogue-1 has pulled the last D1 columns into registers.
 struct FusedArgs {
   const uint8_t *pe_split;   // [(n+1)][PE_ROW_BYTES]
   const int *src_i, *src_j;  // [Epad]
@@ -714,298 +710,6 @@ struct FusedArgs {
   int dbg;
   long long *trace;          // harness only: clock64 timeline of CTA 0 ([role][unit < 8][16]), else nullptr
 };
-
-template <class M>
-struct FusedCfg {
-  static_assert(M::KIND == KIND_BF16, "the fused kernel maps one 32-column epilogue chunk to one BF16 k-chunk");
-  static constexpr int NT1 = 256, NT2 = 128;
-  static constexpr int B1_STAGE = M::NS * NT1 * ROWB;
-  static constexpr int STAGE1 = M::A_STAGE + B1_STAGE;
-  static constexpr int NSTAGE1 = 3;
-  static constexpr int LAG = 2;
-  static constexpr int A2_STAGE = M::A_STAGE;
-  static constexpr int B2_STAGE = M::NS * NT2 * ROWB;
-  static constexpr int OFF_A2 = NSTAGE1 * STAGE1;
-  static constexpr int OFF_W = OFF_A2 + 2 * A2_STAGE;
-  static constexpr int OFF_EXTRA = OFF_W + 2 * B2_STAGE;
-  static constexpr int WARP_PROD0 = NUM_EPI_WARPS, NUM_PROD_WARPS = 4;
-  static constexpr int WARP_LOAD1 = 12, WARP_LOAD2 = 13, WARP_MMA1 = 14, WARP_MMA2 = 15;
-  static constexpr int THREADS = 512;
-  static constexpr int SMEM_EXTRA = 512 + 1024 + (CCSP_HH + CCSP_MAXP * CCSP_HH + CCSP_MAXP) * 4 + SUB_M * CCSP_MAXP * 4;
-  static constexpr int SMEM_BYTES = OFF_EXTRA + SMEM_EXTRA + 1024;
-  static constexpr int D2_COL = 256;
-  static_assert(SMEM_BYTES <= 227 * 1024, "fused kernel does not fit in shared memory");
-};
-
-template <class M>
-__global__ void __launch_bounds__(FusedCfg<M>::THREADS, 1) k_edge_fused_tc(const FusedArgs A) {
-  using C = FusedCfg<M>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t *extra = smem + C::OFF_EXTRA;
-  uint64_t *full1 = reinterpret_cast<uint64_t *>(extra);     // [3]
-  uint64_t *empty1 = full1 + 4;                              // [3]
-  uint64_t *tfull1 = empty1 + 4, *tempty1 = tfull1 + 1;
-  uint64_t *a2_full = tempty1 + 1;                           // [2]
-  uint64_t *a2_empty = a2_full + 2;                          // [2]
-  uint64_t *w_full = a2_empty + 2;                           // [2]
-  uint64_t *w_empty = w_full + 2;                            // [2]
-  uint64_t *tfull2 = w_empty + 2, *tempty2 = tfull2 + 1;
-  uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(tempty2 + 1);
-  float *tb_s = reinterpret_cast<float *>(extra + 512);      // [256]
-  float *bd1 = tb_s + 256;                                   // [128]
-  float *w2t = bd1 + CCSP_HH;                                // [128][8]
-  float *bd2 = w2t + CCSP_MAXP * CCSP_HH;                    // [8]
-  float *red = bd2 + CCSP_MAXP;                              // [128][8]
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_tiles = A.num_m_tiles * 2;
-  const uint32_t smem_base = smem_u32(smem);
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < C::NSTAGE1; ++s) { mbar_init(&full1[s], C::NUM_PROD_WARPS * 32 + 1); mbar_init(&empty1[s], 1); }
-    mbar_init(tfull1, 1); mbar_init(tempty1, EPI_THREADS);
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(&a2_full[s], EPI_THREADS / 2); mbar_init(&a2_empty[s], 1);
-      mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1);
-    }
-    mbar_init(tfull2, 1); mbar_init(tempty2, EPI_THREADS);
-    fence_barrier_init();
-  }
-  if (warp == C::WARP_MMA1) tmem_alloc(tmem_ptr, 512);
-  if (warp < NUM_EPI_WARPS) {
-    for (int i = threadIdx.x; i < CCSP_HH; i += EPI_THREADS) bd1[i] = A.bd1[i];
-    for (int i = threadIdx.x; i < CCSP_MAXP * CCSP_HH; i += EPI_THREADS) {
-      const int j = i / CCSP_MAXP, pp = i % CCSP_MAXP;
-      w2t[i] = pp < A.P ? A.Wd2[pp * CCSP_HH + j] : 0.f;
-    }
-    if (threadIdx.x < CCSP_MAXP) bd2[threadIdx.x] = threadIdx.x < A.P ? A.bd2[threadIdx.x] : 0.f;
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
-
-  if (warp >= C::WARP_PROD0 && warp < C::WARP_PROD0 + C::NUM_PROD_WARPS) {
-    // ============ A gather (as k_edge_l1_tc) =====================================================
-    const int t = threadIdx.x - C::WARP_PROD0 * 32;
-    const int q = t & 3, r0 = t >> 2;
-    uint32_t g = 0, sig = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile >> 1) * SUB_M;
-      size_t roff[4];
-#pragma unroll 1
-      for (int kc = 0; kc < M::NKC1; ++kc, ++g) {
-        if (kc == 0 || kc == M::NKC1 / 2) {
-          const int *idx = kc == 0 ? A.src_i : A.src_j;
-#pragma unroll
-          for (int p = 0; p < 4; ++p) roff[p] = (size_t)__ldg(&idx[m0 + r0 + 32 * p]) * M::PE_ROW_BYTES;
-        }
-        const uint32_t s = g % C::NSTAGE1;
-        mbar_wait(&empty1[s], ((g / C::NSTAGE1) & 1) ^ 1);
-        if (!(A.dbg & 1)) {
-          const uint32_t koff = (uint32_t)(kc % (M::NKC1 / 2)) * ROWB + q * 16;
-          const uint32_t st = smem_base + s * C::STAGE1;
-#pragma unroll
-          for (int p = 0; p < 4; ++p) {
-            const uint8_t *src = A.pe_split + roff[p] + koff;
-            const uint32_t dst = st + sw64_off(r0 + 32 * p, q);
-            cp_async16(dst, src);
-            if (M::NS == 2) cp_async16(dst + PART, src + M::PE_LO_OFF);
-          }
-        }
-        cp_async_commit();
-        if (g - sig >= (uint32_t)C::LAG) {
-          cp_async_wait<C::LAG>();
-          fence_proxy_async();
-          mbar_arrive(&full1[sig % C::NSTAGE1]);
-          ++sig;
-        }
-      }
-    }
-    cp_async_wait<0>();
-    fence_proxy_async();
-    for (; sig < g; ++sig) mbar_arrive(&full1[sig % C::NSTAGE1]);
-  } else if (warp == C::WARP_LOAD1) {
-    // ============ first-layer weight loader ======================================================
-    if (lane == 0) {
-      uint32_t g = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int grp = __ldg(&A.tile_type[tile >> 1]);
-        const uint8_t *blob = A.b_blob + ((size_t)(grp * 2 + (tile & 1)) * M::NKC1) * C::B1_STAGE;
-        for (int kc = 0; kc < M::NKC1; ++kc, ++g) {
-          const uint32_t s = g % C::NSTAGE1;
-          mbar_wait(&empty1[s], ((g / C::NSTAGE1) & 1) ^ 1);
-          if (A.dbg & 2) { mbar_arrive(&full1[s]); continue; }
-          mbar_arrive_expect_tx(&full1[s], C::B1_STAGE);
-          bulk_g2s(smem_base + s * C::STAGE1 + M::A_STAGE, blob + (size_t)kc * C::B1_STAGE, C::B1_STAGE, &full1[s]);
-        }
-      }
-    }
-  } else if (warp == C::WARP_LOAD2) {
-    // ============ decoder weight loader: chunks in GEMM2's consumption order q -> (q&1)*4 + (q>>1) ====
-    if (lane == 0) {
-      uint32_t g2 = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        for (int q = 0; q < 8; ++q, ++g2) {
-          const uint32_t s = g2 & 1;
-          mbar_wait(&w_empty[s], ((g2 >> 1) & 1) ^ 1);
-          if (A.dbg & 2) { mbar_arrive(&w_full[s]); continue; }
-          const int c = (q & 1) * 4 + (q >> 1);
-          mbar_arrive_expect_tx(&w_full[s], C::B2_STAGE);
-          bulk_g2s(smem_base + C::OFF_W + s * C::B2_STAGE, A.w_blob + (size_t)c * C::B2_STAGE, C::B2_STAGE, &w_full[s]);
-        }
-      }
-    }
-  } else if (warp == C::WARP_MMA1) {
-    // ============ GEMM1 issuer ===================================================================
-    if (lane == 0) {
-      uint32_t g = 0, tcount = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
-        mbar_wait(tempty1, (tcount & 1) ^ 1);
-        tc_fence_after();
-        for (int kc = 0; kc < M::NKC1; ++kc, ++g) {
-          const uint32_t s = g % C::NSTAGE1;
-          mbar_wait(&full1[s], (g / C::NSTAGE1) & 1);
-          tc_fence_after();
-          const uint32_t a_hi = smem_base + s * C::STAGE1;
-          if (!(A.dbg & 8)) issue_chunk<M, C::NT1>(tmem_base, a_hi, a_hi + M::A_STAGE, kc == 0);
-          umma_commit(&empty1[s]);
-        }
-        umma_commit(tfull1);
-      }
-    }
-  } else if (warp == C::WARP_MMA2) {
-    // ============ GEMM2 issuer ===================================================================
-    if (lane == 0) {
-      uint32_t g2 = 0, tcount = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
-        mbar_wait(tempty2, (tcount & 1) ^ 1);
-        tc_fence_after();
-        for (int q = 0; q < 8; ++q, ++g2) {
-          const uint32_t grp = q & 1, ws = g2 & 1;
-          const uint32_t u = tcount * 4 + (q >> 1);            // use counter of A2 stage `grp`
-          mbar_wait(&a2_full[grp], u & 1);
-          mbar_wait(&w_full[ws], (g2 >> 1) & 1);
-          tc_fence_after();
-          if (!(A.dbg & 8))
-            issue_chunk<M, C::NT2>(tmem_base + C::D2_COL, smem_base + C::OFF_A2 + grp * C::A2_STAGE,
-                                   smem_base + C::OFF_W + ws * C::B2_STAGE, q == 0);
-          umma_commit(&a2_empty[grp]);
-          umma_commit(&w_empty[ws]);
-        }
-        umma_commit(tfull2);
-      }
-    }
-  } else if (warp < NUM_EPI_WARPS) {
-    // ============ epilogues: warp w <-> TMEM lanes 32 (w & 3).., column group (w >> 2) ================
-    uint32_t tcount = 0;
-    const int quarter = warp & 3, chalf = warp >> 2;
-    const int r = quarter * 32 + lane;
-    uint8_t *a2_stage = smem + C::OFF_A2 + chalf * C::A2_STAGE;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
-      const int mt = tile >> 1, slot = tile & 1;
-      const int grp = __ldg(&A.tile_type[mt]);
-      const size_t row = (size_t)mt * SUB_M + r;
-      const int col0 = slot * 256 + chalf * 128;
-      const float4 *Sblk = reinterpret_cast<const float4 *>(A.S) + (((row >> 5) * 16 + (col0 >> 5)) * 8) * 32 + lane;
-      float4 sn[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) sn[j] = (A.dbg & 4) ? make_float4(0.f, 0.f, 0.f, 0.f) : ldg_nc_f4(Sblk + j * 32);
-      const float tb_mine = __ldg(&A.tb[(size_t)grp * CCSP_H2 + slot * 256 + threadIdx.x]);
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      tb_s[threadIdx.x] = tb_mine;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      // ---- epilogue-1: D1 -> decoder operand chunks ------------------------------------------------
-      mbar_wait(tfull1, tcount & 1);
-      tc_fence_after();
-      const uint32_t taddr1 = tmem_base + chalf * 128 + ((uint32_t)(quarter * 32) << 16);
-#pragma unroll 1
-      for (int cbi = 0; cbi < 4; ++cbi) {
-        float4 sc[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) sc[j] = sn[j];
-        if (cbi < 3 && !(A.dbg & 4)) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) sn[j] = ldg_nc_f4(Sblk + (cbi + 1) * 256 + j * 32);
-        }
-        float v[32];
-        tmem_ld32(taddr1 + cbi * 32, v);
-        if (cbi == 3) {                      // D1 fully in registers: GEMM1 of the next tile may overwrite it
-          tc_fence_before();
-          mbar_arrive(tempty1);
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 t4 = *reinterpret_cast<const float4 *>(&tb_s[chalf * 128 + cbi * 32 + 4 * j]);
-          v[4 * j] = silu_fast(v[4 * j] + sc[j].x + t4.x);
-          v[4 * j + 1] = silu_fast(v[4 * j + 1] + sc[j].y + t4.y);
-          v[4 * j + 2] = silu_fast(v[4 * j + 2] + sc[j].z + t4.z);
-          v[4 * j + 3] = silu_fast(v[4 * j + 3] + sc[j].w + t4.w);
-        }
-        const uint32_t u = tcount * 4 + cbi;
-        mbar_wait(&a2_empty[chalf], (u & 1) ^ 1);          // GEMM2 has consumed this group's previous chunk
-        store_split32<M>(a2_stage, 0, r, v);
-        fence_proxy_async();
-        mbar_arrive(&a2_full[chalf]);
-      }
-      // ---- epilogue-2: D2 -> o ---------------------------------------------------------------------
-      mbar_wait(tfull2, tcount & 1);
-      tc_fence_after();
-      const uint32_t taddr2 = tmem_base + C::D2_COL + chalf * 64 + ((uint32_t)(quarter * 32) << 16);
-      float acc[CCSP_MAXP];
-#pragma unroll
-      for (int p = 0; p < CCSP_MAXP; ++p) acc[p] = 0.f;
-#pragma unroll 1
-      for (int cb = 0; cb < 64; cb += 32) {
-        float v[32];
-        tmem_ld32(taddr2 + cb, v);
-        const int c0 = chalf * 64 + cb;
-        if (A.P <= 4) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float d = silu_fast(v[j] + bd1[c0 + j]);
-            const float4 w = *reinterpret_cast<const float4 *>(&w2t[(c0 + j) * CCSP_MAXP]);
-            acc[0] = fmaf(d, w.x, acc[0]); acc[1] = fmaf(d, w.y, acc[1]); acc[2] = fmaf(d, w.z, acc[2]); acc[3] = fmaf(d, w.w, acc[3]);
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float d = silu_fast(v[j] + bd1[c0 + j]);
-            const float4 w0 = *reinterpret_cast<const float4 *>(&w2t[(c0 + j) * CCSP_MAXP]);
-            const float4 w1 = *reinterpret_cast<const float4 *>(&w2t[(c0 + j) * CCSP_MAXP + 4]);
-            acc[0] = fmaf(d, w0.x, acc[0]); acc[1] = fmaf(d, w0.y, acc[1]); acc[2] = fmaf(d, w0.z, acc[2]); acc[3] = fmaf(d, w0.w, acc[3]);
-            acc[4] = fmaf(d, w1.x, acc[4]); acc[5] = fmaf(d, w1.y, acc[5]); acc[6] = fmaf(d, w1.z, acc[6]); acc[7] = fmaf(d, w1.w, acc[7]);
-          }
-        }
-      }
-      tc_fence_before();
-      mbar_arrive(tempty2);
-      if (chalf == 1) {
-        *reinterpret_cast<float4 *>(&red[r * CCSP_MAXP]) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-        if (A.P > 4) *reinterpret_cast<float4 *>(&red[r * CCSP_MAXP + 4]) = make_float4(acc[4], acc[5], acc[6], acc[7]);
-      }
-      asm volatile("bar.sync 2, 256;" ::: "memory");
-      if (chalf == 0 && !(A.dbg & 4)) {
-        float *orow = A.o + ((size_t)(mt * SUB_M + r) * 2 + slot) * A.P;
-        float res[CCSP_MAXP];
-#pragma unroll
-        for (int p = 0; p < CCSP_MAXP; ++p) res[p] = (acc[p] + red[r * CCSP_MAXP + p]) + bd2[p];
-        if (A.P == 4) {
-          *reinterpret_cast<float4 *>(orow) = make_float4(res[0], res[1], res[2], res[3]);
-        } else {
-#pragma unroll
-          for (int p = 0; p < CCSP_MAXP; ++p)
-            if (p < A.P) orow[p] = res[p];
-        }
-      }
-      asm volatile("bar.sync 3, 256;" ::: "memory");
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == C::WARP_MMA1) tmem_dealloc(tmem_base, 512);
-}
 
 // ---------------------------------------------------------------------------------------------------
 // host: pack a row-major FP32 weight block W[n_rows_total, ldw] (nn.Linear layout, K along columns
@@ -1063,7 +767,10 @@ void pack_b_blob(const float *W, int ldw, int k_begin, int K_total, int n_rows_t
 template <class M, int CL = 1>
 cudaError_t launch_l1_tc(const L1Args &a, int num_sms, cudaStream_t st) {
   using C = L1Cfg<M, CL>;
-  static int max_clusters = 0;
+  static int max_clusters_dev[64] = {};      // per device: function attributes and cluster occupancy
+  int dev_ = 0;
+  cudaGetDevice(&dev_);
+  int &max_clusters = max_clusters_dev[dev_ & 63];
   if (max_clusters == 0) {
     cudaError_t e = cudaFuncSetAttribute(k_edge_l1_tc<M, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) return e;
@@ -1096,7 +803,10 @@ cudaError_t launch_l1_tc(const L1Args &a, int num_sms, cudaStream_t st) {
 template <class M>
 cudaError_t launch_dec_tc(const DecArgs &a, int num_sms, cudaStream_t st) {
   using C = DecCfg<M>;
-  static bool configured = false;
+  static bool configured_dev[64] = {};      // per device: function attributes belong to the device's context
+  int dev_ = 0;
+  cudaGetDevice(&dev_);
+  bool &configured = configured_dev[dev_ & 63];
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(k_edge_dec_tc<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) return e;
@@ -1104,21 +814,6 @@ cudaError_t launch_dec_tc(const DecArgs &a, int num_sms, cudaStream_t st) {
   }
   if (a.num_tiles == 0) return cudaSuccess;
   k_edge_dec_tc<M><<<a.num_tiles < num_sms ? a.num_tiles : num_sms, C::THREADS, C::SMEM_BYTES, st>>>(a);
-  return cudaGetLastError();
-}
-
-template <class M>
-cudaError_t launch_fused_tc(const FusedArgs &a, int num_sms, cudaStream_t st) {
-  using C = FusedCfg<M>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(k_edge_fused_tc<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
-  const int tiles = a.num_m_tiles * 2;
-  if (tiles == 0) return cudaSuccess;
-  k_edge_fused_tc<M><<<tiles < num_sms ? tiles : num_sms, C::THREADS, C::SMEM_BYTES, st>>>(a);
   return cudaGetLastError();
 }
 

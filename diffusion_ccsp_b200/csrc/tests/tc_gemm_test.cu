@@ -190,15 +190,15 @@ static void run_chain(const Problem &p, const std::vector<double> *Href, const s
 static int g_dbg_or = 0;
 static bool g_trace = false;   // OR'ed into the pair kernel's dbg word (256: relay mode)
 // fused kernels: o only (PAIR: CTA-pair / cta_group::2 version)
-template <class M, int PAIR = 0>   // 0: single-CTA fused prototype, 1: CTA pair (cp.async + relay), 2: CTA pair (TMA)
+template <class M, int PAIR = 1>   // 1: CTA pair (cp.async + relay), 2: CTA pair (TMA gather4 / tile loads)
 static void run_fused(const Problem &p, const std::vector<double> *oref, int iters, int sms, Report &o, int dbg = 0) {
   const int rows = p.m_tiles * 128;
   std::vector<float> Sblk((size_t)rows * 512);
   for (int r = 0; r < rows; ++r)
     for (int c = 0; c < 512; ++c) Sblk[blk_off(r, c)] = p.S[(size_t)r * 512 + c];
   std::vector<uint8_t> pe = split_rows<M>(p.node_emb);
-  const size_t per = (size_t)2 * M::NKC1 * FusedCfg<M>::B1_STAGE;
-  std::vector<uint8_t> b1(per * p.groups), b2((size_t)M::NKC2 * FusedCfg<M>::B2_STAGE);
+  const size_t per = (size_t)2 * M::NKC1 * Fused2Cfg<M>::B1_BLOB_STAGE;
+  std::vector<uint8_t> b1(per * p.groups), b2((size_t)M::NKC2 * Fused2Cfg<M>::W_BLOB_STAGE);
   for (int g = 0; g < p.groups; ++g) pack_b_blob<M, 256>(&p.W[(size_t)g * 512 * 512], 512, 0, 512, 512, b1.data() + g * per);
   pack_b_blob<M, 128>(p.Wd1.data(), 256, 0, 256, 128, b2.data());
   uint8_t *d_pe = dev(pe), *d_b1 = dev(b1), *d_b2 = dev(b2);
@@ -214,7 +214,6 @@ static void run_fused(const Problem &p, const std::vector<double> *oref, int ite
   memset(&pm, 0, sizeof(pm));
   if (PAIR == 2) CK((make_pair_maps<M>(&pm, d_pe, (int64_t)(pe.size() / M::PE_ROW_BYTES), d_b1, p.groups, d_b2)));
   auto launch = [&]() -> cudaError_t {
-    if (PAIR == 0) return launch_fused_tc<M>(a, sms, 0);
     return launch_fused2_tc<M>(a, sms, 0, PAIR == 2 ? &pm : nullptr);
   };
   long long *d_tr = nullptr;
@@ -312,8 +311,6 @@ int main(int argc, char **argv) {
     run_chain<Mode<KIND_BF16, 3>, 2>(p, &Href, &oref, 0, sms, h, o); chk("H bf16x3 cl2", h, 2e-5); chk("o bf16x3 cl2", o, 2e-5);
     run_chain<Mode<KIND_BF16, 3>, 4>(p, &Href, &oref, 0, sms, h, o); chk("H bf16x3 cl4", h, 2e-5); chk("o bf16x3 cl4", o, 2e-5);
     run_chain<Mode<KIND_TF32, 3>, 2>(p, &Href, &oref, 0, sms, h, o); chk("H tf32x3 cl2", h, 3e-6); chk("o tf32x3 cl2", o, 3e-6);
-    run_fused<Mode<KIND_BF16, 3>>(p, &oref, 0, sms, o); chk("o fused bf16x3", o, 2e-5);
-    run_fused<Mode<KIND_BF16, 1>>(p, &oref, 0, sms, o); chk("o fused bf16", o, 4e-2);
     }
     run_fused<Mode<KIND_BF16, 3>, 1>(p, &oref, 0, sms, o); chk("o pair bf16x3", o, 2e-5);
     run_fused<Mode<KIND_BF16, 1>, 1>(p, &oref, 0, sms, o); chk("o pair bf16", o, 4e-2);
@@ -359,17 +356,11 @@ int main(int argc, char **argv) {
     {
       Report f;
       const double ff = fl1 + fdec;
-      run_fused<Mode<KIND_BF16, 3>>(p, nullptr, 20, sms, f); printf("%-30s fused %.3f ms %6.1f TFLOP/s\n", "bf16x3 fused", f.ms, ff / f.ms / 1e9);
-      run_fused<Mode<KIND_BF16, 1>>(p, nullptr, 20, sms, f); printf("%-30s fused %.3f ms %6.1f TFLOP/s\n", "bf16 fused", f.ms, ff / f.ms / 1e9);
       run_fused<Mode<KIND_BF16, 3>, 1>(p, nullptr, 20, sms, f); printf("%-30s fused %.3f ms %6.1f TFLOP/s\n", "bf16x3 pair", f.ms, ff / f.ms / 1e9);
       run_fused<Mode<KIND_BF16, 1>, 1>(p, nullptr, 20, sms, f); printf("%-30s fused %.3f ms %6.1f TFLOP/s\n", "bf16 pair", f.ms, ff / f.ms / 1e9);
       for (int dbg : {1, 2, 4, 7, 8, 15}) {
         run_fused<Mode<KIND_BF16, 3>, 1>(p, nullptr, 10, sms, f, dbg);
         printf("bf16x3 pair dbg=%-2d               fused %.3f ms %6.1f TFLOP/s\n", dbg, f.ms, ff / f.ms / 1e9);
-      }
-      for (int dbg : {1, 2, 4, 7, 8, 15}) {
-        run_fused<Mode<KIND_BF16, 3>>(p, nullptr, 10, sms, f, dbg);
-        printf("bf16x3 fused dbg=%-2d              fused %.3f ms %6.1f TFLOP/s\n", dbg, f.ms, ff / f.ms / 1e9);
       }
     }
     const char *abl[16] = {"none", "noA", "noB", "noA,noB", "noEpiIO", "noA,noEpiIO", "noB,noEpiIO", "MMA+sync only",
