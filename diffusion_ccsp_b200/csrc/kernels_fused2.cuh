@@ -122,8 +122,21 @@ __device__ __forceinline__ void bulk_g2s_rbar(uint32_t dst, const void *src, uin
 __device__ __forceinline__ void cp_async_arrive_noinc(uint64_t *bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void prefetch_l2_bulk(const void *src, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+// The static term S (166 MB) streams through the 126 MB L2 once per evaluation; marking it evict-first keeps the
+// hot set (weights 13.6 MB, pose embeddings 9.4 MB) resident, so ring fetches do not pay HBM latency.
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void prefetch_l2_bulk(const void *src, uint32_t bytes, uint64_t policy) {
+  asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(src), "r"(bytes), "l"(policy) : "memory");
+}
+__device__ __forceinline__ float4 ldg_nc_f4_hint(const float4 *p, uint64_t policy) {
+  float4 v;
+  asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(policy));
+  return v;
 }
 // (CTA-scope acquire on purpose: a cluster-scope acquire costs an L1 invalidate (CCTL.IVALL) per wait, ~400 cycles in the
 // issue loops; what crosses CTAs here are barrier signals, the operand bytes are read by each SM's own tensor core.)
@@ -568,6 +581,7 @@ k_edge_fused2_tc(const FusedArgs A, const __grid_constant__ PairMaps maps) {
     const uint32_t r_tempty1 = mapa_u32(smem_u32(tempty1), 0);
     const uint32_t r_tempty2_0 = mapa_u32(smem_u32(&tempty2[0]), 0), r_tempty2_1 = mapa_u32(smem_u32(&tempty2[1]), 0);
     const uint32_t r_a2_full = mapa_u32(smem_u32(&a2_full[cg]), 0);
+    const uint64_t pol_s = l2_policy_evict_first();
     // ---- epilogue-2 of unit itp (deferred by one unit: GEMM2 had a whole GEMM1 to finish): D2 -> o -------
     auto epi2 = [&](uint32_t itp, size_t rowp, int slotp) {
       if (itp == 0) pdl_wait();          // o is still being read by the preceding node kernel until it completes
@@ -653,13 +667,13 @@ k_edge_fused2_tc(const FusedArgs A, const __grid_constant__ PairMaps maps) {
       // S in the blocked layout: 32-row x 32-col blocks of 8 pieces x 32 lanes x 16 B (coalesced 512 B / instruction)
       const float4 *Sblk = reinterpret_cast<const float4 *>(A.S) + (((row >> 5) * 16 + (gcol0 >> 5)) * 8) * 32 + lane;
       const bool noS = (A.dbg & 4) != 0;
-      float4 sa = noS ? make_float4(0.f, 0.f, 0.f, 0.f) : ldg_nc_f4(Sblk), sb = noS ? sa : ldg_nc_f4(Sblk + 32);
+      float4 sa = noS ? make_float4(0.f, 0.f, 0.f, 0.f) : ldg_nc_f4_hint(Sblk, pol_s), sb = noS ? sa : ldg_nc_f4_hint(Sblk + 32, pol_s);
       if (threadIdx.x < 4 && u + unit_step < num_units && !(A.dbg & 4)) {
         // next unit's slice of S (4 row blocks x 32 KB contiguous) -> L2, so the register prefetch below only
         // has to cover an L2 hit
         const int un = u + unit_step;
         const size_t rb = (size_t)((un >> 1) * 2 + (int)rank) * 4 + threadIdx.x;
-        prefetch_l2_bulk(A.S + (rb * 16 + (size_t)(un & 1) * 8) * 1024, 32768);
+        prefetch_l2_bulk(A.S + (rb * 16 + (size_t)(un & 1) * 8) * 1024, 32768, pol_s);
       }
       float *tbu = tb_s + (it & 1) * 256;
       if (threadIdx.x < 256) tbu[threadIdx.x] = __ldg(&A.tb[(size_t)grp * CCSP_H2 + slot * 256 + threadIdx.x]);
@@ -689,7 +703,7 @@ k_edge_fused2_tc(const FusedArgs A, const __grid_constant__ PairMaps maps) {
           const float4 ca = sa, cb = sb;
           if (pi < 7 && !noS) {                      // S of the next piece, one step ahead
             const float4 *nx = Sblk + ((pi + 1) >> 2) * 256 + ((pi + 1) & 3) * 64;
-            sa = ldg_nc_f4(nx); sb = ldg_nc_f4(nx + 32);
+            sa = ldg_nc_f4_hint(nx, pol_s); sb = ldg_nc_f4_hint(nx + 32, pol_s);
           }
           const float4 ta = *reinterpret_cast<const float4 *>(&tbu[cg * 64 + pi * 8]);
           const float4 tb4 = *reinterpret_cast<const float4 *>(&tbu[cg * 64 + pi * 8 + 4]);
@@ -737,6 +751,12 @@ cudaError_t launch_fused2_impl(const FusedArgs &a, const PairMaps &maps, int num
   if (max_clusters == 0) {
     cudaError_t e = cudaFuncSetAttribute(k_edge_fused2_tc<M, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) return e;
+    // setmaxnreg moves registers inside the pool the CTA was launched with; if the compiler ever allocated fewer than
+    // the re-partition needs, the epilogue warps would wait for registers forever — refuse to launch instead
+    cudaFuncAttributes fa;
+    e = cudaFuncGetAttributes(&fa, k_edge_fused2_tc<M, TMA>);
+    if (e != cudaSuccess) return e;
+    if (fa.numRegs * C::THREADS < C::NUM_EPI * 32 * C::EPI_REGS + (C::THREADS - C::NUM_EPI * 32) * C::AUX_REGS) return cudaErrorLaunchOutOfResources;
     cudaLaunchConfig_t q = {};
     q.gridDim = dim3(num_sms / 2 * 2); q.blockDim = dim3(C::THREADS); q.dynamicSmemBytes = C::SMEM_BYTES;
     cudaLaunchAttribute at[1];
