@@ -381,16 +381,22 @@ k_edge_fused2_tc(const FusedArgs A, const __grid_constant__ PairMaps maps) {
             if (A.dbg & 1) { if (lane == 0) mbar_arrive_remote(rfull[s]); continue; }
             if (lane == 0) mbar_arrive_expect_tx_remote(rfull[s], M::A_STAGE);
             const uint32_t dst = smem_base + s * C::STAGE1 + lane * 4 * ROWB;
-            const int col = (kc % (M::NKC1 / 2)) * M::KC;
+            const int col = M::pe_off(kc % (M::NKC1 / 2), 0, 0) / M::ELT;       // element column of the hi slice; lo = + KC
             tma_gather4_pair(dst, &maps.pe, col, idx.x, idx.y, idx.z, idx.w, rfull[s]);
-            if (M::NS == 2) tma_gather4_pair(dst + PART, &maps.pe, CCSP_H + col, idx.x, idx.y, idx.z, idx.w, rfull[s]);
+            if (M::NS == 2) tma_gather4_pair(dst + PART, &maps.pe, col + M::KC, idx.x, idx.y, idx.z, idx.w, rfull[s]);
           }
         }
       }
     } else {
-    // ============ A gather: this CTA's 128 edges; thread = (piece q, rows r0 + 32 p) ==================
+    // ============ A gather: this CTA's 128 edges ========================================================
+    // x3 split: thread = (piece q8 of the row's 128 contiguous bytes [hi 64 | lo 64] of this k-chunk, rows r0 + 16 p);
+    // a warp instruction covers 4 rows x 128 B = 4 cache lines / 4 shared-memory wavefronts.  Single pass: hi only.
     const int t = threadIdx.x - C::WARP_PROD0 * 32;
-    const int q = t & 3, r0 = t >> 2;
+    constexpr int LPR = M::NS == 2 ? 8 : 4;        // lanes per row
+    constexpr int RPP = 128 / LPR;                 // rows per pass
+    constexpr int NP = SUB_M / RPP;                // passes (= cp.async per thread and chunk)
+    const int q8 = t % LPR, r0 = t / LPR;
+    const int part = q8 >> 2, q = q8 & 3;
     // Completion is signalled by the copy engine itself (cp.async.mbarrier.arrive.noinc: one arrival per thread
     // when all its earlier cp.async have landed), so a thread never waits for data and all NSTAGE1 stages can be
     // in flight; the peer's barrier is forwarded to the leader by the relay lane below.
@@ -398,27 +404,23 @@ k_edge_fused2_tc(const FusedArgs A, const __grid_constant__ PairMaps maps) {
     pdl_wait();                          // pe_split is written by the preceding node kernel
     for (int u = unit0; u < num_units; u += unit_step, ++it) {
       const int m0 = ((u >> 1) * 2 + (int)rank) * SUB_M;
-      size_t roff[4];
+      uint32_t roff[NP];                 // row offsets in 16-byte units (row stride 1 KB: fits 32 bits up to 4 M nodes)
 #pragma unroll 1
       for (int kc = 0; kc < M::NKC1; ++kc, ++g) {
         if (kc == 0 || kc == M::NKC1 / 2) {
           const int *idx = kc == 0 ? A.src_i : A.src_j;
 #pragma unroll
-          for (int p = 0; p < 4; ++p) roff[p] = (size_t)__ldg(&idx[m0 + r0 + 32 * p]) * M::PE_ROW_BYTES;
+          for (int p = 0; p < NP; ++p) roff[p] = (uint32_t)__ldg(&idx[m0 + r0 + RPP * p]) * (M::PE_ROW_BYTES / 16);
         }
         const uint32_t s = g % C::NSTAGE1;
         mbar_wait(&empty1[s], ((g / C::NSTAGE1) & 1) ^ 1);
         if (t == 0) TR(6, kc);
         if (!(A.dbg & 1)) {
-          const uint32_t koff = (uint32_t)(kc % (M::NKC1 / 2)) * ROWB + q * 16;
-          const uint32_t st = smem_base + s * C::STAGE1;
+          const uint32_t koff = M::pe_off(kc % (M::NKC1 / 2), part, q);
+          const uint32_t st = smem_base + s * C::STAGE1 + part * PART;
 #pragma unroll
-          for (int p = 0; p < 4; ++p) {
-            const uint8_t *src = A.pe_split + roff[p] + koff;
-            const uint32_t dst = st + sw64_off(r0 + 32 * p, q);
-            cp_async16(dst, src);
-            if (M::NS == 2) cp_async16(dst + PART, src + M::PE_LO_OFF);
-          }
+          for (int p = 0; p < NP; ++p)
+            cp_async16(st + sw64_off(r0 + RPP * p, q), A.pe_split + (size_t)roff[p] * 16 + koff);
         }
         cp_async_arrive_noinc(&full1[s]);
         if (t == 0) TR(7, kc);

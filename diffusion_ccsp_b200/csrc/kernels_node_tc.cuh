@@ -361,10 +361,14 @@ __global__ void __launch_bounds__(NodeTcCfg<M>::THREADS, 1) k_node_tc(const Node
       if (vv > A.n) break;
       const uint8_t *src = smem + (size_t)rr * M::PE_ROW_BYTES;
       uint8_t *dst = reinterpret_cast<uint8_t *>(A.pe) + (size_t)vv * M::PE_ROW_BYTES;
-      const uint4 a0 = *reinterpret_cast<const uint4 *>(src + (((lane + rr) & 63) << 4));
-      const uint4 a1 = *reinterpret_cast<const uint4 *>(src + (((lane + 32 + rr) & 63) << 4));
-      *reinterpret_cast<uint4 *>(dst + (lane << 4)) = a0;
-      *reinterpret_cast<uint4 *>(dst + ((lane + 32) << 4)) = a1;
+      // global 16-byte slot g of the row holds piece (g & 3) of part ((g >> 2) & 1) of k-chunk (g >> 3)  (Mode::pe_off);
+      // the staged row is [hi chunks 0..31 | lo chunks 32..63], rotated by the row index
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int gs = lane + 32 * h;
+        const int c = ((gs >> 2) & 1) * 32 + (gs >> 3) * 4 + (gs & 3);
+        *reinterpret_cast<uint4 *>(dst + (gs << 4)) = *reinterpret_cast<const uint4 *>(src + (((c + rr) & 63) << 4));
+      }
     }
   }
   NTR(10);

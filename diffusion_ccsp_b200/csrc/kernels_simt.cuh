@@ -320,12 +320,13 @@ __global__ void __launch_bounds__(NODE_THREADS) k_node(NodeArgs A) {
         for (int c = 0; c < 4; ++c) g[c] = __bfloat162float(__float2bfloat16_rn(e[c]));
         __nv_bfloat162 h01 = __floats2bfloat162_rn(g[0], g[1]), h23 = __floats2bfloat162_rn(g[2], g[3]);
         __nv_bfloat162 l01 = __floats2bfloat162_rn(e[0] - g[0], e[1] - g[1]), l23 = __floats2bfloat162_rn(e[2] - g[2], e[3] - g[3]);
-        __nv_bfloat16 *row = reinterpret_cast<__nv_bfloat16 *>(A.pe) + (size_t)v * (2 * CCSP_H);
+        // BF16 row layout: per 32-element k-chunk [hi 32 | lo 32]  (kernels_tc.cuh Mode::pe_off)
+        __nv_bfloat16 *row = reinterpret_cast<__nv_bfloat16 *>(A.pe) + (size_t)v * (2 * CCSP_H) + (col >> 5) * 64 + (col & 31);
         uint2 hv, lv;
         hv.x = *reinterpret_cast<uint32_t *>(&h01); hv.y = *reinterpret_cast<uint32_t *>(&h23);
         lv.x = *reinterpret_cast<uint32_t *>(&l01); lv.y = *reinterpret_cast<uint32_t *>(&l23);
-        *reinterpret_cast<uint2 *>(row + col) = hv;
-        *reinterpret_cast<uint2 *>(row + CCSP_H + col) = lv;
+        *reinterpret_cast<uint2 *>(row) = hv;
+        *reinterpret_cast<uint2 *>(row + 32) = lv;
       }
     }
   }

@@ -184,9 +184,20 @@ struct Mode {
   static constexpr int KSTEPS = 2;                           // tcgen05.mma K (8 / 16 elements = 32 B) per stage
   static constexpr int NS = NSPLIT == 3 ? 2 : 1;             // operand parts per stage (hi[, lo])
   static constexpr int A_STAGE = NS * PART;
-  // split pose embedding row written by the node kernel: [256 hi][256 lo] operand elements
-  static constexpr int PE_LO_OFF = CCSP_H * ELT;
+  // split pose embedding row written by the node kernel.
+  //   TF32: [256 hi][256 lo] operand words.
+  //   BF16: per 64-byte k-chunk (32 elements) [hi 64 B | lo 64 B], 8 chunks: the hi and lo slices one ring stage needs
+  //         from a gathered row are 128 contiguous bytes = one cache line and one shared-memory wavefront per row,
+  //         instead of two half lines (the 16-byte cp.async gather costs a wavefront per distinct global segment).
   static constexpr int PE_ROW_BYTES = 2 * CCSP_H * ELT;
+  // byte offset, inside a row, of 16-byte piece q (0..3) of operand part `part` (0 hi, 1 lo) of k-chunk kc (of the 256 dims)
+  __host__ __device__ static constexpr int pe_off(int kc, int part, int q) {
+    return KIND == KIND_TF32 ? part * (CCSP_H * ELT) + kc * ROWB + q * 16 : kc * (2 * ROWB) + part * ROWB + q * 16;
+  }
+  // byte offset of element k (0..255) of part `part`
+  __host__ __device__ static constexpr int pe_elem_off(int k, int part) {
+    return pe_off(k / KC, part, (k % KC) * ELT / 16) + ((k % KC) * ELT) % 16;
+  }
   static constexpr int NKC1 = CCSP_H2 / KC;                  // first layer: K = 512
   static constexpr int NKC2 = CCSP_H / KC;                   // decoder:     K = 256
   // bytes of H (operand format) per 128-row x 256-K decoder tile
@@ -404,14 +415,14 @@ __global__ void __launch_bounds__(L1Cfg<M, CL>::THREADS, 1) k_edge_l1_tc(const L
         const uint32_t s = g % C::NSTAGE;
         mbar_wait(&empty_bar[s], ((g / C::NSTAGE) & 1) ^ 1);
         if (!(A.dbg & 1)) {
-          const uint32_t koff = (uint32_t)(kc % (M::NKC1 / 2)) * ROWB + q * 16;
+          const int kcl = kc % (M::NKC1 / 2);
           const uint32_t st = smem_base + s * C::STAGE;
 #pragma unroll
           for (int p = 0; p < 4; ++p) {
-            const uint8_t *src = A.pe_split + roff[p] + koff;
+            const uint8_t *src = A.pe_split + roff[p];
             const uint32_t dst = st + sw64_off(r0 + 32 * p, q);
-            cp_async16(dst, src);
-            if (M::NS == 2) cp_async16(dst + PART, src + M::PE_LO_OFF);
+            cp_async16(dst, src + M::pe_off(kcl, 0, q));
+            if (M::NS == 2) cp_async16(dst + PART, src + M::pe_off(kcl, 1, q));
           }
         }
         cp_async_commit();

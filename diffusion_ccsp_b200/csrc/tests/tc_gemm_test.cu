@@ -86,10 +86,10 @@ static std::vector<uint8_t> split_rows(const std::vector<float> &emb) {
         uint32_t hi = host_tf32_rna(x);
         float hf; memcpy(&hf, &hi, 4);
         uint32_t lo = host_tf32_rna(x - hf);
-        memcpy(row + k * 4, &hi, 4); memcpy(row + M::PE_LO_OFF + k * 4, &lo, 4);
+        memcpy(row + M::pe_elem_off(k, 0), &hi, 4); memcpy(row + M::pe_elem_off(k, 1), &lo, 4);
       } else {
         uint16_t hi = host_bf16_rn(x), lo = host_bf16_rn(x - host_bf16_to_f(hi));
-        memcpy(row + k * 2, &hi, 2); memcpy(row + M::PE_LO_OFF + k * 2, &lo, 2);
+        memcpy(row + M::pe_elem_off(k, 0), &hi, 2); memcpy(row + M::pe_elem_off(k, 1), &lo, 2);
       }
     }
   return out;
