@@ -10,6 +10,7 @@
 
 #include "../kernels_tc.cuh"
 #include "../kernels_fused2.cuh"
+#include "../kernels_fused3.cuh"
 
 namespace ccsp {
 void set_error(const std::string &) {}
@@ -190,7 +191,7 @@ static void run_chain(const Problem &p, const std::vector<double> *Href, const s
 static int g_dbg_or = 0;
 static bool g_trace = false;   // OR'ed into the pair kernel's dbg word (256: relay mode)
 // fused kernels: o only (PAIR: CTA-pair / cta_group::2 version)
-template <class M, int PAIR = 1>   // 1: CTA pair (cp.async + relay), 2: CTA pair (TMA gather4 / tile loads)
+template <class M, int PAIR = 1>   // 1: CTA pair (cp.async + relay), 2: CTA pair (TMA gather4 / tile loads), 3: decoder operand in TMEM
 static void run_fused(const Problem &p, const std::vector<double> *oref, int iters, int sms, Report &o, int dbg = 0) {
   const int rows = p.m_tiles * 128;
   std::vector<float> Sblk((size_t)rows * 512);
@@ -214,6 +215,7 @@ static void run_fused(const Problem &p, const std::vector<double> *oref, int ite
   memset(&pm, 0, sizeof(pm));
   if (PAIR == 2) CK((make_pair_maps<M>(&pm, d_pe, (int64_t)(pe.size() / M::PE_ROW_BYTES), d_b1, p.groups, d_b2)));
   auto launch = [&]() -> cudaError_t {
+    if (PAIR == 3) return launch_fused3_tc<M>(a, sms, 0);
     return launch_fused2_tc<M>(a, sms, 0, PAIR == 2 ? &pm : nullptr);
   };
   long long *d_tr = nullptr;
@@ -314,6 +316,8 @@ int main(int argc, char **argv) {
     }
     run_fused<Mode<KIND_BF16, 3>, 1>(p, &oref, 0, sms, o); chk("o pair bf16x3", o, 2e-5);
     run_fused<Mode<KIND_BF16, 1>, 1>(p, &oref, 0, sms, o); chk("o pair bf16", o, 4e-2);
+    run_fused<Mode<KIND_BF16, 3>, 3>(p, &oref, 0, sms, o); chk("o pairTMEM bf16x3", o, 2e-5);
+    run_fused<Mode<KIND_BF16, 1>, 3>(p, &oref, 0, sms, o); chk("o pairTMEM bf16", o, 4e-2);
     run_fused<Mode<KIND_BF16, 3>, 2>(p, &oref, 0, sms, o); chk("o pairTMA bf16x3", o, 2e-5);
     run_fused<Mode<KIND_BF16, 1>, 2>(p, &oref, 0, sms, o); chk("o pairTMA bf16", o, 4e-2);
   }
@@ -333,6 +337,12 @@ int main(int argc, char **argv) {
       for (int dbg : {1, 2, 4, 7, 8, 15}) {
         run_fused<Mode<KIND_BF16, 3>, 1>(p, nullptr, 10, sms, f, dbg);
         printf("bf16x3 pair dbg=%-2d               fused %.3f ms %6.1f TFLOP/s\n", dbg, f.ms, ff / f.ms / 1e9);
+      }
+      run_fused<Mode<KIND_BF16, 3>, 3>(p, nullptr, 20, sms, f); printf("%-30s fused %.3f ms %6.1f TFLOP/s\n", "bf16x3 pair TMEM-A2", f.ms, ff / f.ms / 1e9);
+      run_fused<Mode<KIND_BF16, 1>, 3>(p, nullptr, 20, sms, f); printf("%-30s fused %.3f ms %6.1f TFLOP/s\n", "bf16 pair TMEM-A2", f.ms, ff / f.ms / 1e9);
+      for (int dbg : {1, 2, 4, 7, 8, 15}) {
+        run_fused<Mode<KIND_BF16, 3>, 3>(p, nullptr, 10, sms, f, dbg);
+        printf("bf16x3 pair TMEM-A2 dbg=%-2d       fused %.3f ms %6.1f TFLOP/s\n", dbg, f.ms, ff / f.ms / 1e9);
       }
       run_fused<Mode<KIND_BF16, 3>, 2>(p, nullptr, 20, sms, f); printf("%-30s fused %.3f ms %6.1f TFLOP/s\n", "bf16x3 pair TMA", f.ms, ff / f.ms / 1e9);
       run_fused<Mode<KIND_BF16, 1>, 2>(p, nullptr, 20, sms, f); printf("%-30s fused %.3f ms %6.1f TFLOP/s\n", "bf16 pair TMA", f.ms, ff / f.ms / 1e9);
