@@ -214,7 +214,9 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
-        # keep stdout to the one JSON line: with NCCL_DEBUG >= VERSION set in the environment NCCL prints its banner there
+        # keep stdout to the one JSON line: the image exports NCCL_DEBUG=VERSION, which makes NCCL printf its banner there
+        if os.environ.get('NCCL_DEBUG', '').upper() == 'VERSION':
+            del os.environ['NCCL_DEBUG']
         os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
         dist.init_process_group('nccl', device_id=dev)
 
