@@ -1,22 +1,22 @@
 // kernels_fused3.cuh — EXPERIMENT (harness only, not used by the library): the CTA-pair edge kernel with the decoder's
-// A operand in TENSOR MEMORY.  Result on B200 (csrc/tests/tc_gemm_test.cu pair): numerically identical to
-// k_edge_fused2_tc, GEMM1 reaches the tensor-bound cadence (15.6 k cycles per unit incl. the interleaved GEMM2), but the
-// kernel as a whole is slower (0.133 ms vs 0.120 ms): with D2 single-buffered the epilogue has to wait for GEMM2 of the
-// unit it has just fed (queued behind the next GEMM1 on the tensor pipe), and holding 64 D1 values across epilogue-2
-// spills.  Kept because the pieces work (tcgen05.st of packed BF16 as an MMA A operand, TS-form cta_group::2 MMA) and the
-// TMEM budget, not the idea, is what blocks it: D1 256 + D2 2 x 128 leaves no columns for the operand slots.
+// A operand in TENSOR MEMORY.
 //
-// Same computation and the same operand formats as kernels_fused2.cuh (k_edge_fused2_tc); what changes is how the
-// first-layer activations reach GEMM2.  fused2 writes them (hi / lo BF16) into a 64 KB shared-memory ring and GEMM2 reads
-// them back three times as an SS MMA.  ncu shows that kernel limited by the shared-memory data pipe (tensor operand reads
-// 36 % + LSU 29 % of peak with the tensor pipe at 70 %, profiles/README.md §3).  Here the epilogue stores the packed BF16
-// activations to tensor memory with tcgen05.st and GEMM2 takes its A operand from there (tcgen05.mma [d], [a_tmem], b):
+// Same computation and operand formats as k_edge_fused2_tc; what changes is how the first-layer activations reach GEMM2.
+// fused2 writes them (hi / lo BF16) into a 64 KB shared-memory ring and GEMM2 reads them back three times as an SS MMA, and
+// ncu shows that kernel limited by the shared-memory data pipe (profiles/README.md §3).  Here epilogue-1 stores the packed
+// BF16 activations to tensor memory (tcgen05.st) and GEMM2 takes its A operand from there (TS-form cta_group::2 MMA):
 //   * no shared-memory stores / proxy fences in epilogue-1, no A reads of GEMM2 from shared memory;
-//   * the 64 KB of the operand ring become two more stages of ring 1 (6 x 32 KB), which covers the L2 latency of the
-//     operand stream (4 stages did not);
-//   * TMEM: D1 = columns 0..255, D2 = 256..383 (single: epilogue-2 of a unit follows its epilogue-1 directly, GEMM2 of the
-//     next unit cannot start before GEMM1 of that unit is done anyway), decoder operand slots = 384..511:
-//     8 slots of 16 columns (one k-step: 8 columns hi + 8 columns lo, two BF16 per column), two per epilogue column group.
+//   * the 64 KB of the operand ring become a fifth stage of ring 1 and a 6-deep decoder-weight ring;
+//   * TMEM: D1 = columns 0..255, D2 = 256..383 (SINGLE-buffered), decoder operand slots = 384..511: 8 slots of 16 columns
+//     (one k-step: 8 columns hi + 8 columns lo, two BF16 per column), two per epilogue column group;
+//   * epilogue-2 runs in four warps of its own (a thread owns a whole row of D2: no cross-warp reduction).
+//
+// Result on B200 (csrc/tests/tc_gemm_test.cu pair): numerically identical to fused2; GEMM1 reaches the tensor-bound cadence
+// (15.6 k cycles per unit incl. the interleaved GEMM2, vs 18.5 k in fused2) — but 0.127 ms vs 0.122 ms overall.  What blocks
+// it is the TMEM budget, not the idea: D1 256 + operand slots 128 leave room for ONE D2, so GEMM2 of the next unit has to wait
+// until epilogue-2 has drained D2 (8 k cycles with 56 registers per thread), GEMM2 completes 2-4 k cycles after its last
+// k-step because it queues behind the next GEMM1 on the tensor pipe, and the stall propagates to epilogue-1 through the
+// operand slots.  fused2's double-buffered D2 + deferred epilogue-2 hides exactly that latency.
 #pragma once
 #include "kernels_fused2.cuh"
 
@@ -52,13 +52,15 @@ struct Fused3Cfg {
   static constexpr int NW = 6;                                // of the 8 chunks a unit consumes: practically resident
   static constexpr int OFF_W = NSTAGE1 * STAGE1;
   static constexpr int OFF_EXTRA = OFF_W + NW * W_STAGE;
-  static constexpr int NUM_EPI = 16, EPI_T = NUM_EPI * 32;
-  static constexpr int WARP_PROD0 = NUM_EPI, NUM_PROD_WARPS = 4;
-  static constexpr int WARP_LOAD = 20, WARP_MMA1 = 21, WARP_MMA2 = 22, WARP_LOADW = 23;
-  static constexpr int THREADS = 24 * 32;                     // 768
-  static constexpr int EPI_REGS = 104, AUX_REGS = 32;         // 768 x 80 = 512 x 104 + 256 x 32
-  // barriers 512 | tb_s 2x256 | bd1 128 | w2t 128x8 | bd2 16 | red 3x128 float4
-  static constexpr int SMEM_EXTRA = 512 + (512 + CCSP_HH + CCSP_MAXP * CCSP_HH + 16) * 4 + 3 * SUB_M * 16;
+  static constexpr int NUM_EPI = 16, EPI_T = NUM_EPI * 32;    // epilogue-1 warps
+  static constexpr int WARP_EPI2_0 = NUM_EPI, NUM_EPI2 = 4;   // epilogue-2 warps (one per TMEM lane quarter)
+  static constexpr int WARP_PROD0 = WARP_EPI2_0 + NUM_EPI2, NUM_PROD_WARPS = 4;
+  static constexpr int WARP_LOAD = 24, WARP_MMA1 = 25, WARP_MMA2 = 26, WARP_LOADW = 27;
+  static constexpr int THREADS = 28 * 32;                     // 896
+  // register pool = 896 x 72: 512 x 96 (epilogue-1) + 128 x 56 (epilogue-2) + 128 x 32 (gather) + 128 x 32 (loaders, issuers)
+  static constexpr int EPI_REGS = 96, EPI2_REGS = 56, AUX_REGS = 32;
+  // barriers 512 | tb_s 2x256 | bd1 128 | w2t 128x8 | bd2 16
+  static constexpr int SMEM_EXTRA = 512 + (512 + CCSP_HH + CCSP_MAXP * CCSP_HH + 16) * 4;
   static constexpr int SMEM_BYTES = OFF_EXTRA + SMEM_EXTRA + 1024;
   static constexpr int D2_COL = 256, A2_COL = 384;
   static_assert(SMEM_BYTES <= 227 * 1024, "kernel does not fit in shared memory");
@@ -83,7 +85,6 @@ __global__ void __launch_bounds__(Fused3Cfg<M>::THREADS, 1) k_edge_fused3_tc(con
   float *bd1 = tb_s + 512;                                   // [128]
   float *w2t = bd1 + CCSP_HH;                                // [128][8]
   float *bd2 = w2t + CCSP_MAXP * CCSP_HH;                    // [8] (+8 pad)
-  float4 *red = reinterpret_cast<float4 *>(bd2 + 16);        // [3][128]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -101,11 +102,11 @@ __global__ void __launch_bounds__(Fused3Cfg<M>::THREADS, 1) k_edge_fused3_tc(con
     for (int s = 0; s < 8; ++s) { mbar_init(&a2_full[s], 8); mbar_init(&a2_empty[s], 1); }
     for (int s = 0; s < C::NW; ++s) { mbar_init(&w_full[s], leader ? 2 : 1); mbar_init(&w_empty[s], 1); }
     mbar_init(tfull1, 1); mbar_init(tempty1, 2 * C::NUM_EPI);
-    mbar_init(tfull2, 1); mbar_init(tempty2, 2 * C::NUM_EPI);
+    mbar_init(tfull2, 1); mbar_init(tempty2, 2 * C::NUM_EPI2);
     fence_barrier_init();
   }
   if (warp == C::WARP_MMA1) tmem_alloc2(tmem_ptr, 512);
-  if (warp < C::NUM_EPI) {
+  if (warp < C::NUM_EPI) {     // tables of epilogue-2
     for (int i = threadIdx.x; i < CCSP_HH; i += C::EPI_T) bd1[i] = A.bd1[i];
     for (int i = threadIdx.x; i < CCSP_MAXP * CCSP_HH; i += C::EPI_T) {
       const int j = i / CCSP_MAXP, pp = i % CCSP_MAXP;
@@ -121,8 +122,67 @@ __global__ void __launch_bounds__(Fused3Cfg<M>::THREADS, 1) k_edge_fused3_tc(con
 
 #define REG_DEC() asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(C::AUX_REGS))
 #define REG_INC() asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(C::EPI_REGS))
+#define REG_DEC2() asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(C::EPI2_REGS))
 
-  if (warp >= C::WARP_PROD0 && warp < C::WARP_PROD0 + C::NUM_PROD_WARPS) {
+  if (warp >= C::WARP_EPI2_0 && warp < C::WARP_EPI2_0 + C::NUM_EPI2) {
+    REG_DEC2();
+    // ============ epilogue-2 (own warps): D2 -> + b -> SiLU -> 128 -> P -> o.  A thread owns a whole row, so there is no
+    // cross-warp reduction; D2 is single-buffered, and these warps drain it while GEMM1 of the next unit runs, long before
+    // GEMM2 of that unit can start.
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const uint32_t r_tempty2 = mapa_u32(smem_u32(tempty2), 0);
+    uint32_t it = 0;
+    for (int u = unit0; u < num_units; u += unit_step, ++it) {
+      const int mt = (u >> 1) * 2 + (int)rank, slot = u & 1;
+      const size_t row = (size_t)mt * SUB_M + r;
+      mbar_wait_cl(tfull2, it & 1);
+      if (it == 0) pdl_wait();               // o is still being read by the preceding node kernel until it completes
+      tc_fence_after();
+      const uint32_t taddr2 = tmem_base + C::D2_COL + ((uint32_t)(quarter * 32) << 16);
+      float acc[CCSP_MAXP];
+#pragma unroll
+      for (int p = 0; p < CCSP_MAXP; ++p) acc[p] = bd2[p];
+#pragma unroll 1
+      for (int hc = 0; hc < 8; ++hc) {
+        float v2[16];
+        tmem_ld16(taddr2 + hc * 16, v2);
+        if (hc == 7) {                       // D2 fully read: GEMM2 of the next unit may overwrite it
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_remote(r_tempty2);
+        }
+        const int c0 = hc * 16;
+        if (A.P <= 4) {
+#pragma unroll
+          for (int jj = 0; jj < 16; ++jj) {
+            const float d = silu_raw(v2[jj] + bd1[c0 + jj]);
+            const float4 w = *reinterpret_cast<const float4 *>(&w2t[(c0 + jj) * CCSP_MAXP]);
+            acc[0] = fmaf(d, w.x, acc[0]); acc[1] = fmaf(d, w.y, acc[1]); acc[2] = fmaf(d, w.z, acc[2]); acc[3] = fmaf(d, w.w, acc[3]);
+          }
+        } else {
+#pragma unroll
+          for (int jj = 0; jj < 16; ++jj) {
+            const float d = silu_raw(v2[jj] + bd1[c0 + jj]);
+            const float4 w0 = *reinterpret_cast<const float4 *>(&w2t[(c0 + jj) * CCSP_MAXP]);
+            const float4 w1 = *reinterpret_cast<const float4 *>(&w2t[(c0 + jj) * CCSP_MAXP + 4]);
+            acc[0] = fmaf(d, w0.x, acc[0]); acc[1] = fmaf(d, w0.y, acc[1]); acc[2] = fmaf(d, w0.z, acc[2]); acc[3] = fmaf(d, w0.w, acc[3]);
+            acc[4] = fmaf(d, w1.x, acc[4]); acc[5] = fmaf(d, w1.y, acc[5]); acc[6] = fmaf(d, w1.z, acc[6]); acc[7] = fmaf(d, w1.w, acc[7]);
+          }
+        }
+      }
+      if (!(A.dbg & 4)) {
+        float *orow = A.o + ((size_t)row * 2 + slot) * A.P;
+        if (A.P == 4) {
+          *reinterpret_cast<float4 *>(orow) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        } else {
+#pragma unroll
+          for (int p = 0; p < CCSP_MAXP; ++p)
+            if (p < A.P) orow[p] = acc[p];
+        }
+      }
+    }
+  } else if (warp >= C::WARP_PROD0 && warp < C::WARP_PROD0 + C::NUM_PROD_WARPS) {
     REG_DEC();
     // ============ A gather (as in k_edge_fused2_tc): this CTA's 128 edges =================================
     const int t = threadIdx.x - C::WARP_PROD0 * 32;
@@ -292,81 +352,9 @@ __global__ void __launch_bounds__(Fused3Cfg<M>::THREADS, 1) k_edge_fused3_tc(con
     const int quarter = warp & 3, cg = warp >> 2;
     const int r = quarter * 32 + lane;
     const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
-    const uint32_t r_tempty1 = mapa_u32(smem_u32(tempty1), 0), r_tempty2 = mapa_u32(smem_u32(tempty2), 0);
+    const uint32_t r_tempty1 = mapa_u32(smem_u32(tempty1), 0);
     const uint32_t r_a2_full0 = mapa_u32(smem_u32(&a2_full[2 * cg]), 0), r_a2_full1 = mapa_u32(smem_u32(&a2_full[2 * cg + 1]), 0);
     const uint64_t pol_s = l2_policy_evict_first();
-    // ---- epilogue-2 of unit itp: D2 -> o.  It runs between the D1 drain and the epilogue-1 arithmetic of the NEXT unit
-    // (the thread is holding 64 D1 values then, hence 16-column chunks): GEMM1 of the unit after that is already running,
-    // and GEMM2 of unit itp, which queues behind GEMM1 on the tensor pipe, has had a whole unit to finish.
-    auto epi2 = [&](uint32_t itp, size_t rowp, int slotp) {
-      mbar_wait_cl(tfull2, itp & 1);
-      if (itp == 0) pdl_wait();              // o is still being read by the preceding node kernel until it completes
-      tc_fence_after();
-      const uint32_t taddr2 = tmem_base + C::D2_COL + cg * 32 + lane_sel;
-      float acc[CCSP_MAXP];
-#pragma unroll
-      for (int p = 0; p < CCSP_MAXP; ++p) acc[p] = 0.f;
-#pragma unroll 1
-      for (int hc = 0; hc < 2; ++hc) {
-        float v2[16];
-        tmem_ld16(taddr2 + hc * 16, v2);
-        if (hc == 1) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_remote(r_tempty2);
-        }
-        const int c0 = cg * 32 + hc * 16;
-        if (A.P <= 4) {
-#pragma unroll
-          for (int jj = 0; jj < 16; ++jj) {
-            const float d = silu_raw(v2[jj] + bd1[c0 + jj]);
-            const float4 w = *reinterpret_cast<const float4 *>(&w2t[(c0 + jj) * CCSP_MAXP]);
-            acc[0] = fmaf(d, w.x, acc[0]); acc[1] = fmaf(d, w.y, acc[1]); acc[2] = fmaf(d, w.z, acc[2]); acc[3] = fmaf(d, w.w, acc[3]);
-          }
-        } else {
-#pragma unroll
-          for (int jj = 0; jj < 16; ++jj) {
-            const float d = silu_raw(v2[jj] + bd1[c0 + jj]);
-            const float4 w0 = *reinterpret_cast<const float4 *>(&w2t[(c0 + jj) * CCSP_MAXP]);
-            const float4 w1 = *reinterpret_cast<const float4 *>(&w2t[(c0 + jj) * CCSP_MAXP + 4]);
-            acc[0] = fmaf(d, w0.x, acc[0]); acc[1] = fmaf(d, w0.y, acc[1]); acc[2] = fmaf(d, w0.z, acc[2]); acc[3] = fmaf(d, w0.w, acc[3]);
-            acc[4] = fmaf(d, w1.x, acc[4]); acc[5] = fmaf(d, w1.y, acc[5]); acc[6] = fmaf(d, w1.z, acc[6]); acc[7] = fmaf(d, w1.w, acc[7]);
-          }
-        }
-      }
-      // column groups 1..3 hand their partial sums to group 0 (fixed order -> deterministic)
-      float *orow = A.o + ((size_t)rowp * 2 + slotp) * A.P;
-      if (cg > 0) red[(cg - 1) * SUB_M + r] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-      asm volatile("bar.sync 2, 512;" ::: "memory");
-      if (cg == 0 && !(A.dbg & 4)) {
-        const float4 r1 = red[r], r2 = red[SUB_M + r], r3 = red[2 * SUB_M + r];
-        float res[4] = {((acc[0] + r1.x) + r2.x) + r3.x + bd2[0], ((acc[1] + r1.y) + r2.y) + r3.y + bd2[1],
-                        ((acc[2] + r1.z) + r2.z) + r3.z + bd2[2], ((acc[3] + r1.w) + r2.w) + r3.w + bd2[3]};
-        if (A.P == 4) {
-          *reinterpret_cast<float4 *>(orow) = make_float4(res[0], res[1], res[2], res[3]);
-        } else {
-#pragma unroll
-          for (int p = 0; p < 4; ++p)
-            if (p < A.P) orow[p] = res[p];
-        }
-      }
-      asm volatile("bar.sync 2, 512;" ::: "memory");      // red may be rewritten (second round / next call)
-      if (A.P > 4) {                                // second round for components 4..7 (robot poses, P = 5)
-        if (cg > 0) red[(cg - 1) * SUB_M + r] = make_float4(acc[4], acc[5], acc[6], acc[7]);
-        asm volatile("bar.sync 2, 512;" ::: "memory");
-        if (cg == 0 && !(A.dbg & 4)) {
-          const float4 r1 = red[r], r2 = red[SUB_M + r], r3 = red[2 * SUB_M + r];
-          float res[4] = {((acc[4] + r1.x) + r2.x) + r3.x + bd2[4], ((acc[5] + r1.y) + r2.y) + r3.y + bd2[5],
-                          ((acc[6] + r1.z) + r2.z) + r3.z + bd2[6], ((acc[7] + r1.w) + r2.w) + r3.w + bd2[7]};
-#pragma unroll
-          for (int p = 0; p < 4; ++p)
-            if (4 + p < A.P) orow[4 + p] = res[p];
-        }
-        asm volatile("bar.sync 2, 512;" ::: "memory");
-      }
-    };
-    size_t prev_row = 0;
-    int prev_slot = 0;
     uint32_t it = 0;
     for (int u = unit0; u < num_units; u += unit_step, ++it) {
       const int mt = (u >> 1) * 2 + (int)rank, slot = u & 1;
@@ -400,9 +388,6 @@ __global__ void __launch_bounds__(Fused3Cfg<M>::THREADS, 1) k_edge_fused3_tc(con
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(r_tempty1);
       if (tron) TR(trole, 3);
-      if (it > 0) epi2(it - 1, prev_row, prev_slot);
-      prev_row = row; prev_slot = slot;
-      if (tron) TR(trole, 9);
 #pragma unroll
       for (int ks4 = 0; ks4 < 4; ++ks4) {            // 16 columns = one k-step of the decoder
         uint32_t hi[8], lo[8];
@@ -440,7 +425,6 @@ __global__ void __launch_bounds__(Fused3Cfg<M>::THREADS, 1) k_edge_fused3_tc(con
       }
       if (tron) TR(trole, 10);
     }
-    if (it > 0) epi2(it - 1, prev_row, prev_slot);
   }
 #undef TR
 #undef REG_DEC
@@ -465,7 +449,7 @@ cudaError_t launch_fused3_tc(const FusedArgs &a, int num_sms, cudaStream_t st) {
     cudaFuncAttributes fa;
     e = cudaFuncGetAttributes(&fa, k_edge_fused3_tc<M>);
     if (e != cudaSuccess) return e;
-    if (fa.numRegs * C::THREADS < C::NUM_EPI * 32 * C::EPI_REGS + (C::THREADS - C::NUM_EPI * 32) * C::AUX_REGS) return cudaErrorLaunchOutOfResources;
+    if (fa.numRegs * C::THREADS < C::NUM_EPI * 32 * C::EPI_REGS + C::NUM_EPI2 * 32 * C::EPI2_REGS + 8 * 32 * C::AUX_REGS) return cudaErrorLaunchOutOfResources;
     cudaLaunchConfig_t q = {};
     q.gridDim = dim3(num_sms / 2 * 2); q.blockDim = dim3(C::THREADS); q.dynamicSmemBytes = C::SMEM_BYTES;
     cudaLaunchAttribute at[1];
