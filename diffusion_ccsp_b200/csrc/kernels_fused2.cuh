@@ -584,6 +584,11 @@ k_edge_fused2_tc(const FusedArgs A, const __grid_constant__ PairMaps maps) {
     const uint32_t r_tempty2_0 = mapa_u32(smem_u32(&tempty2[0]), 0), r_tempty2_1 = mapa_u32(smem_u32(&tempty2[1]), 0);
     const uint32_t r_a2_full = mapa_u32(smem_u32(&a2_full[cg]), 0);
     const uint64_t pol_s = l2_policy_evict_first();
+    if (threadIdx.x < 4 && unit0 < num_units && !(A.dbg & 4)) {
+      // first unit's slice of S -> L2 while the ring fills (S is a plan constant: no need to wait for the previous kernel)
+      const size_t rb = (size_t)((unit0 >> 1) * 2 + (int)rank) * 4 + threadIdx.x;
+      prefetch_l2_bulk(A.S + (rb * 16 + (size_t)(unit0 & 1) * 8) * 1024, 32768, pol_s);
+    }
     // ---- epilogue-2 of unit itp (deferred by one unit: GEMM2 had a whole GEMM1 to finish): D2 -> o -------
     auto epi2 = [&](uint32_t itp, size_t rowp, int slotp) {
       if (itp == 0) pdl_wait();          // o is still being read by the preceding node kernel until it completes
