@@ -327,6 +327,7 @@ k_edge_fused2_tc(const FusedArgs A, const __grid_constant__ PairMaps maps) {
 #define TR(role, slot) do { if (tr && it < 8) tr[((role) * 8 + it) * 16 + (slot)] = clock64(); } while (0)
 #define TRP(role, slot) do { if (tr && itp < 8) tr[((role) * 8 + itp) * 16 + (slot)] = clock64(); } while (0)
 
+  const long long t_entry = tr ? clock64() : 0;
   if (threadIdx.x == 0) pdl_launch_dependents();
   if (threadIdx.x == 0) {
     // ring 1: own gather threads + own weight loader (+ at the leader: the peer's relay lane)
@@ -489,6 +490,7 @@ k_edge_fused2_tc(const FusedArgs A, const __grid_constant__ PairMaps maps) {
       if (leader) {
         // ============ GEMM1 issuer (M = 256 over the pair) =============================================
         uint32_t g = 0, it = 0;
+        if (tr) tr[15] = t_entry;          // kernel entry of this thread (slot 15 of MMA1 / unit 0)
         for (int u = unit0; u < num_units; u += unit_step, ++it) {
           TR(0, 0);
           mbar_wait_cl(tempty1, (it & 1) ^ 1);

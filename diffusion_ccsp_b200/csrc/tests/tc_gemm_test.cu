@@ -231,9 +231,9 @@ static void run_fused(const Problem &p, const std::vector<double> *oref, int ite
     CK(cudaMemcpy(tr.data(), d_tr, tr.size() * sizeof(long long), cudaMemcpyDeviceToHost));
     const char *names[8] = {"MMA1", "MMA2", "EPI w0", "EPI w12", "M1 wait", "M1 cmt", "G empty", "G issue"};
     long long t0 = tr[0];
-    printf("trace (dbg %d), cycles relative to MMA1 unit-0 start; columns = trace slots\n", a.dbg);
+    printf("trace (dbg %d), cycles relative to MMA1 unit-0 start; columns = trace slots; kernel entry at %lld\n", a.dbg, tr[15] ? tr[15] - t0 : 0);
     for (int role = 0; role < 8; ++role)
-      for (int it = (role < 4 ? 0 : 3); it < (role < 4 ? 8 : 5); ++it) {
+      for (int it = 0; it < (role < 4 ? 8 : 2); ++it) {
         printf("  %-7s u%d:", names[role], it);
         for (int sl = 0; sl < (role < 4 ? 11 : 16); ++sl) { long long v = tr[(role * 8 + it) * 16 + sl]; if (v) printf(" %7lld", v - t0); else printf("       -"); }
         printf("\n");
