@@ -134,7 +134,7 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void *src, uint32_t bytes
 }
 __device__ __forceinline__ float4 ldg_nc_f4_hint(const float4 *p, uint64_t policy) {
   float4 v;
-  asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
                : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(policy));
   return v;
 }
