@@ -17,8 +17,10 @@
 //   GEMM2  D2[128 x 128] (TMEM cols 256.., double buffered) <- those chunks x pose_decoder.0 chunks
 //   epi-2  same 16 warps: D2 -> +b -> SiLU -> 128 -> P FMAs -> o
 //
-// D1 is single-buffered: GEMM1 of the next unit starts when epi-1 has pulled the last D1 columns into
-// registers; GEMM2 of the current unit fills that window on the tensor pipe.
+// D1 is single-buffered: every epilogue thread pulls its whole share of D1 (64 values) into registers with two TMEM
+// loads and releases the accumulator at once (setmaxnreg gives the 16 epilogue warps 104 registers), so GEMM1 of the next
+// unit starts ~650 cycles after the commit.  D2 is double-buffered and epilogue-2 is deferred by one unit: GEMM2's MMAs
+// queue behind the next GEMM1 on the tensor pipe, and the epilogue never waits for them.
 //
 //   warps 0-15   epilogues (warp w: TMEM lanes 32 (w & 3).., column group w >> 2)
 //   warps 16-19  A gather (cp.async 16 B pieces through the edge index)
@@ -267,7 +269,6 @@ struct Fused2Cfg {
   static constexpr int B1_BLOB_STAGE = M::NS * B1_BLOB_PART;
   static constexpr int STAGE1 = M::A_STAGE + B1_STAGE;        // 32 KB (x3 split)
   static constexpr int NSTAGE1 = 4;
-  static constexpr int LAG = 2;
   static constexpr int A2_STAGE = M::A_STAGE;                 // one decoder k-chunk of 128 rows: 16 KB
   static constexpr int NA2 = 4;                               // one stage per epilogue column group
   static constexpr int W_PART = (NT2 / 2) * ROWB;             // this CTA's 64 decoder-weight rows of one part: 4 KB
