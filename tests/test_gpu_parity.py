@@ -382,3 +382,24 @@ def test_high_degree_nodes_trajectory_vs_oracle(case, math):
     out = gd.sample(batch, noise=noise).cpu().numpy()
     record(f'hub_{mode}_traj_T{T}_K{K}', math, rel_err(out, ref))
     assert rel_err(out, ref) < TOL[math]['traj'], rel_err(out, ref)
+
+
+@pytest.mark.parametrize('math', EXACT_MATHS)
+@pytest.mark.parametrize('P', [1, 3, 7, 8])
+def test_generic_pose_widths_vs_oracle(P, math):
+    """Pose widths outside the reference's three configurations (2, 4, 5) take the run-time-P variants of the node and
+    edge kernels: forward and a short ULA trajectory against the oracle."""
+    mode, dims = 'diffuse_pairwise', ((2, 0, 2), (P, 2, 2 + P))
+    rng = np.random.default_rng(P)
+    sd = synthetic.make_state_dict(dims, mode, seed=P)
+    parts = [scenes.random_typed_scene(rng, n_obj, 2, n_edges, 2 + P) for n_obj, n_edges in ((3, 20), (9, 40), (40, 90))]
+    batch = scenes.collate(parts)
+    m, gd = build(mode, dims, sd, T=3, K=2, math=math)
+    poses = rng.standard_normal((batch.num_nodes, P)).astype(np.float32)
+    ref = oracle_forward(sd, dims, mode, batch, poses, 2)
+    out = m(torch.from_numpy(poses), batch, torch.tensor([2])).cpu().numpy()
+    assert rel_err(out, ref) < TOL[math]['fwd'], rel_err(out, ref)
+    noise = synthetic.make_noise(3, 2, batch.num_nodes, P, seed=5)
+    o = orc.OracleDiffusion(orc.OracleDenoiser(np_sd(sd), dims, mode), 3, 'ULA', 2).p_sample_loop(batch, noise.numpy())
+    out = gd.sample(batch, noise=noise).cpu().numpy()
+    assert rel_err(out, o) < TOL[math]['traj'], rel_err(out, o)
