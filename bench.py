@@ -133,12 +133,47 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------------
-# CPU arm: the oracle (numpy restatement pinned to the reference) on the host cores
+# CPU arm: the reference's OWN implementation (unmodified networks/{ddpm,denoise_fn}.py, staged under oracle/_ref by
+# `python -m oracle.make_ref`, loaded through oracle/ref_shim.py) on all host cores; the numpy port only if it is absent
 # --------------------------------------------------------------------------------------------------
-def cpu_sample_time(batch, sd, dims, mode, T_full, K, timesteps_sampled=1):
-    """Time `timesteps_sampled` timesteps (each 1+K denoiser evaluations) of the real loop at the full
-    batch on the host and extrapolate to T_full (per-timestep cost does not depend on t: same graph,
-    same K — SURVEY.md §8d).  Returns (seconds_per_full_run, seconds_measured)."""
+def reference_sample_time(batch, sd, dims, mode, T_full, K, timesteps_sampled=1, device='cpu', warm=0):
+    """Time `GaussianDiffusion.sample` of the UNMODIFIED reference for `timesteps_sampled` timesteps (each 1+K denoiser
+    evaluations: p_sample + K ULA steps) at the full batch and extrapolate to T_full: the per-timestep cost does not
+    depend on t (same graph, same K — SURVEY.md §8d).  The sampled timesteps are the LAST ones of the T_full cosine
+    schedule (passed as `betas`).  Returns (seconds_per_full_run, seconds_measured, kind)."""
+    import torch
+    from oracle import ref_shim
+    if not ref_shim.reference_available():
+        full, dt = port_sample_time(batch, sd, dims, mode, T_full, K, timesteps_sampled)
+        return full, dt, 'port'
+    dfn, ddpm = ref_shim.load_reference()
+    if device == 'cpu':
+        torch.set_num_threads(os.cpu_count() or 1)
+    m = dfn.ConstraintDiffuser(dims=dims, hidden_dim=256, input_mode=mode, EBM='ULA', device=device, verbose=False)
+    betas = torch.tensor(ddpm.cosine_beta_schedule(T_full)[-timesteps_sampled:])
+    gd = ddpm.GaussianDiffusion(m, timesteps=timesteps_sampled, EBM='ULA', samples_per_step=K, betas=betas,
+                                step_sizes='2*self.betas')
+    if device != 'cpu':
+        gd = gd.to(device)
+    gd.eval()
+    missing, unexpected = gd.load_state_dict(sd, strict=False)
+    assert not unexpected and not [k for k in missing if k.startswith('denoise_fn.')], (missing, unexpected)
+    sync = (lambda: torch.cuda.synchronize()) if device != 'cpu' else (lambda: None)
+    try:
+        for _ in range(warm):
+            gd.sample(batch)
+        sync()
+        t0 = time.perf_counter()
+        gd.sample(batch)                           # the reference's public entry point (ddpm.py:342-351)
+        sync()
+        dt = time.perf_counter() - t0
+    finally:
+        torch.set_grad_enabled(True)               # p_sample_loop flips the global flag (ddpm.py:262-265)
+    return dt / timesteps_sampled * T_full, dt, 'reference'
+
+
+def port_sample_time(batch, sd, dims, mode, T_full, K, timesteps_sampled=1):
+    """Fallback when oracle/_ref is missing: the numpy restatement (oracle/ccsp_oracle.py), same sampling protocol."""
     from oracle import ccsp_oracle as orc
     from diffusion_ccsp_b200 import synthetic
     den = orc.OracleDenoiser({k: v.numpy() for k, v in sd.items()}, dims, mode)
@@ -151,13 +186,19 @@ def cpu_sample_time(batch, sd, dims, mode, T_full, K, timesteps_sampled=1):
     return dt / timesteps_sampled * T_full, dt
 
 
-def host_threads():
+def cpu_model():
     try:
-        from threadpoolctl import threadpool_info
-        n = max([d.get('num_threads', 1) for d in threadpool_info()] + [1])
-        return int(n)
+        for ln in open('/proc/cpuinfo'):
+            if ln.startswith('model name'):
+                return ln.split(':', 1)[1].strip()
     except Exception:
-        return os.cpu_count() or 1
+        pass
+    return 'unknown'
+
+
+def host_threads():
+    import torch
+    return int(torch.get_num_threads())
 
 
 def run_reference(args):
@@ -169,25 +210,35 @@ def run_reference(args):
     sd = synthetic.make_trained_state_dict()
     batch = scenes.qualitative_batch(args.batch, WORKLOAD['n_obj'])
     T, K = args.timesteps, WORKLOAD['K']
-    import oracle.ccsp_oracle  # noqa: F401  (warm numpy/BLAS)
-    times = []
+    times, kind = [], None
     for i in range(args.warmup + args.steps):
-        full, _ = cpu_sample_time(batch, sd, dims, mode, T, K, 1)
+        full, _, kind = reference_sample_time(batch, sd, dims, mode, T, K, 1)
         if i >= args.warmup:
             times.append(full)
     sec = sum(times) / len(times)
     val = args.batch / sec
     cores = host_threads()
-    sample = f'1 of {T} timesteps (11 denoiser evaluations) at the full batch of {args.batch} scenes per step, extrapolated x{T}'
+    sample = (f'each step = GaussianDiffusion.sample over 1 of {T} timesteps (11 denoiser evaluations) at the full batch of '
+              f'{args.batch} scenes, extrapolated x{T} (per-timestep cost is t-independent); ms_per_step is the extrapolated '
+              f'full-run time, not the wall time of the step')
     line = dict(impl='reference', metric='scenes_per_sec', value=val, unit='scenes/s', n_gpus=args.gpus, steps=args.steps,
                 warmup=args.warmup, ms_per_step=sec * 1e3, higher_is_better=True, scaling='weak', vs_baseline=None,
                 dtype='fp32', data='synthetic',
-                config=dict(workload=workload_name(args), timesteps=T, ula_steps=K, scenes=args.batch,
-                            note='CPU arm always runs one replica of the per-GPU workload on rank 0'),
-                cpu_baseline=dict(value=val, unit='scenes/s', cores=cores, kind='port', sample=sample),
+                config=config_dict(args, T, K, args.batch),
+                cpu_baseline=dict(value=val, unit='scenes/s', cores=cores, kind=kind, sample=sample, cpu=cpu_model(),
+                                  code=('unmodified networks/{ddpm,denoise_fn}.py via oracle/_ref, torch %s, %d threads'
+                                        % (__import__('torch').__version__, cores)) if kind == 'reference' else
+                                  'oracle/ccsp_oracle.py numpy port (oracle/_ref missing: run python -m oracle.make_ref)',
+                                  note='one CPU replica of the per-GPU workload on rank 0, whatever --gpus is'),
                 e2e=dict(value=val, unit='scenes/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 gpu_launches=0)
     print(json.dumps(line), flush=True)
+
+
+def config_dict(args, T, K, B):
+    """identical in both arms (the driver compares the dicts)"""
+    return dict(workload=workload_name(args), timesteps=T, ula_steps=K, scenes_per_gpu=B,
+                denoiser_evals_per_step=T * (1 + K))
 
 
 def workload_name(args):
@@ -339,18 +390,29 @@ def run_ours(args):
                               '3-term split: algorithmic FLOPs counted once; ceiling = 1/3 of the tensor peak of the operand type'))
         line = dict(metric='scenes_per_sec', value=value, unit='scenes/s', n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=ms, higher_is_better=True, scaling='weak', vs_baseline=None, dtype=math, data='synthetic',
-                    config=dict(workload=workload_name(args), timesteps=T, ula_steps=K, scenes_per_gpu=B, nodes_per_gpu=n,
-                                edges_per_gpu=E, denoiser_evals_per_step=evals, weights='seeded init, 74k parameters (pose encoder/decoder, mlps biases) trained offline with the reference loss; 9.15 M params',
+                    config=config_dict(args, T, K, B),
+                    workload_detail=dict(nodes_per_gpu=n, edges_per_gpu=E, weights='seeded init, 74k parameters (pose encoder/decoder, mlps biases) trained offline with the reference loss; 9.15 M params',
                                 noise='in-kernel Philox4x32-10', l2='explicit 256 MiB flush between steps; static term + activations (2 x %d MB) exceed L2' % (plan.edge_rows * 512 * 4 >> 20)),
                     clocks=clocks, e2e=e2e, gpu_launches=int(launches), result=result_stats,
                     roofline=roofline,
                     kernels=dict(avg_ms=dict(edge_l1=l1_ms, edge_dec=dec_ms, node=node_ms),
-                                 share_of_step=dict(edge_l1=l1_ms * evals / ms, edge_dec=dec_ms * evals / ms, node=node_ms * evals / ms)),
+                                 share_of_step=dict(edge_l1=l1_ms * evals / ms, edge_dec=dec_ms * evals / ms, node=node_ms * evals / ms),
+                                 shares_additive=False,
+                                 shares_note='the sampling events serialise the PDL-overlapped node/edge pair, so the shares sum to more than 1'),
                     algorithmic_tflops=fl['total'] * evals * world / (ms * 1e-3) / 1e12)
         if world == 1 and not args.no_cpu_baseline:
-            full, measured = cpu_sample_time(batch, sd, dims, mode, T, K, 1)
-            line['cpu_baseline'] = dict(value=B / full, unit='scenes/s', cores=host_threads(), kind='port',
+            full, measured, kind = reference_sample_time(batch, sd, dims, mode, T, K, 1)
+            line['cpu_baseline'] = dict(value=B / full, unit='scenes/s', cores=host_threads(), kind=kind, cpu=cpu_model(),
                                         sample=f'1 of {T} timesteps (11 denoiser evaluations, {measured:.1f} s) at the full batch, extrapolated x{T}')
+            if kind == 'reference':
+                # the tougher baseline of BASELINE.md §3: the same unmodified PyTorch code with device='cuda' on this B200
+                try:
+                    full_c, meas_c, _ = reference_sample_time(batch, sd, dims, mode, T, K, 2, device='cuda', warm=1)
+                    line['reference_cuda'] = dict(value=B / full_c, unit='scenes/s', kind='reference',
+                                                  sample=f'2 of {T} timesteps ({meas_c * 1e3:.0f} ms) after 1 warm-up sample, extrapolated',
+                                                  code='unmodified networks/{ddpm,denoise_fn}.py, device=cuda, torch eager FP32 (allow_tf32 off)')
+                except Exception as ex:      # never let the extra baseline break the bench line
+                    line['reference_cuda'] = dict(unavailable=repr(ex)[:200])
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

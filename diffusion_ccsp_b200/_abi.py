@@ -247,7 +247,8 @@ class Plan:
 
     def close(self):
         if getattr(self, '_h', None):
-            self._lib.ccsp_plan_destroy(self._h)
+            with torch.cuda.device(self.model.device):      # destroy synchronises the plan's device, not the caller's
+                self._lib.ccsp_plan_destroy(self._h)
             self._h = None
 
     def __del__(self):

@@ -25,6 +25,8 @@ NVCC_FLAGS = [
     '-Xcompiler', '-fPIC', '-shared',
     '-Xptxas', '-v',
 ]
+if os.environ.get('CCSP_DEBUG') == '1':      # development builds: mbarrier spin loops trap after 2^22 polls instead of hanging
+    NVCC_FLAGS.append('-DCCSP_DEBUG_SPIN_TRAP')
 
 
 def _nvcc() -> str:

@@ -41,7 +41,7 @@ struct BlockCache {
   std::vector<std::pair<void *, size_t>> blocks;
   size_t bytes = 0;
   static constexpr size_t kCap = (size_t)8 << 30;
-  void *take(size_t need) {
+  void *take(size_t need, size_t *actual) {
     int best = -1;
     for (int i = 0; i < (int)blocks.size(); ++i)
       if (blocks[i].second >= need && blocks[i].second <= 2 * need + ((size_t)1 << 20) &&
@@ -49,6 +49,7 @@ struct BlockCache {
         best = i;
     if (best < 0) return nullptr;
     void *p = blocks[best].first;
+    *actual = blocks[best].second;
     bytes -= blocks[best].second;
     blocks.erase(blocks.begin() + best);
     return p;
@@ -71,10 +72,11 @@ struct DevPool {   // owns device allocations of a model / plan
   template <typename T>
   cudaError_t alloc(T **out, size_t count) {
     size_t bytes = ((count ? count : 1) * sizeof(T) + 255) & ~(size_t)255;
-    void *p = cache ? cache->take(bytes) : nullptr;
+    size_t actual = bytes;        // a cached block can be larger than the request: keep its real size on record
+    void *p = cache ? cache->take(bytes, &actual) : nullptr;
     cudaError_t e = cudaSuccess;
-    if (!p) e = cudaMalloc(&p, bytes);
-    if (e == cudaSuccess) ptrs.emplace_back(p, bytes);
+    if (!p) { actual = bytes; e = cudaMalloc(&p, bytes); }
+    if (e == cudaSuccess) ptrs.emplace_back(p, actual);
     *out = (T *)p;
     return e;
   }
@@ -155,6 +157,7 @@ struct CcspModel {
 
 struct CcspPlan {
   CcspModel *m = nullptr;
+  int device = 0;                 // the model's device, kept so that destroy works after the model is gone
   int64_t n = 0, E = 0, Epad = 0;
   int num_tiles = 0;
   DevPool pool;
@@ -263,7 +266,7 @@ static int model_build(CcspModel *m, const CcspModelDesc *d) {
 // time-term table tb[t][c][:] for t < T  (run-constant: depends on the weights and t only)
 static int ensure_time_table(CcspModel *m, int T, cudaStream_t st) {
   if (T <= m->tb_T) return CCSP_OK;
-  if (m->tb) { CCSP_CUDA_TRY(cudaStreamSynchronize(st)); m->pool.release(m->tb); m->tb = nullptr; m->tb_T = 0; }
+  if (m->tb) { CCSP_CUDA_TRY(cudaDeviceSynchronize()); m->pool.release(m->tb);   /* other streams may still read the old table */ m->tb = nullptr; m->tb_T = 0; }
   float *temb = nullptr;
   CCSP_CUDA_TRY(cudaMalloc(&temb, (size_t)T * CCSP_H * sizeof(float)));
   CCSP_CUDA_TRY(m->pool.alloc(&m->tb, (size_t)T * m->C * CCSP_H2));
@@ -442,7 +445,8 @@ static int launch_node(CcspPlan *p, const NodeArgs &a, cudaStream_t st) {
       NodeArgs b = a;
       b.trace = d;
       CCSP_CUDA_TRY(cudaStreamSynchronize(st));
-      CCSP_CUDA_TRY((tc::launch_node_tc<tc::Mode<tc::KIND_BF16, 3>>(b, p->m->blob_pose[math], st)));
+      if (math == CCSP_MATH_BF16X3) CCSP_CUDA_TRY((tc::launch_node_tc<tc::Mode<tc::KIND_BF16, 3>>(b, p->m->blob_pose[math], st)));
+      else CCSP_CUDA_TRY((tc::launch_node_tc<tc::Mode<tc::KIND_BF16, 1>>(b, p->m->blob_pose[math], st)));
       CCSP_CUDA_TRY(cudaStreamSynchronize(st));
       CCSP_CUDA_TRY(cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost));
       cudaFree(d);
@@ -589,7 +593,7 @@ int ccsp_plan_create(CcspModel *m, const float *x, int64_t n, int32_t F, const i
   g_upload_bytes = 0;
   CcspPlan *p = new CcspPlan();
   p->pool.cache = &m->cache;
-  p->m = m; p->n = n; p->E = E; p->Epad = Epad; p->num_tiles = (int)tile_type.size();
+  p->m = m; p->device = m->device; p->n = n; p->E = E; p->Epad = Epad; p->num_tiles = (int)tile_type.size();
   auto fail = [&](int rc) { p->pool.free_all(); delete p; return rc; };
 #define PLAN_TRY(expr)                                                                             \
   do {                                                                                             \
@@ -658,6 +662,9 @@ int ccsp_plan_create(CcspModel *m, const float *x, int64_t n, int32_t F, const i
 
 void ccsp_plan_destroy(CcspPlan *p) {
   if (!p) return;
+  int prev = 0;
+  cudaGetDevice(&prev);
+  cudaSetDevice(p->device);       // the caller's current device need not be the plan's
   cudaDeviceSynchronize();        // the blocks go back to the model's cache and may be reused at once
   if (p->m) {
     auto &v = p->m->plans;
@@ -667,6 +674,7 @@ void ccsp_plan_destroy(CcspPlan *p) {
   for (cudaEvent_t e : p->ev) cudaEventDestroy(e);
   p->pool.free_all();
   delete p;
+  cudaSetDevice(prev);
 }
 
 int64_t ccsp_plan_num_nodes(const CcspPlan *p) { return p ? p->n : -1; }

@@ -163,7 +163,7 @@ __device__ __forceinline__ bool mbar_test_wait(uint64_t *bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait_cl(uint64_t *bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait_cl(bar, parity)) {
-    if (++spins > SPIN_LIMIT) __trap();
+    CCSP_SPIN_GUARD(spins);
   }
 }
 __device__ __forceinline__ void tmem_alloc2(uint32_t *dst_smem, uint32_t ncols) {

@@ -37,7 +37,15 @@ constexpr int SUB_M = 128;               // rows per tile = TMEM lanes of one ac
 constexpr int PART = SUB_M * ROWB;       // bytes of one operand part (hi or lo) of an A stage: 8 KB
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int EPI_THREADS = NUM_EPI_WARPS * 32;
-constexpr uint32_t SPIN_LIMIT = 1u << 22;   // bounded spin: a protocol bug traps instead of hanging the GPU
+// Bounded spin is a DEBUG aid (build with CCSP_DEBUG=1 -> -DCCSP_DEBUG_SPIN_TRAP): a protocol bug then traps instead of
+// hanging the GPU.  Release builds spin without a limit: a legitimate stall (debugger, MPS time slice, preemption) must not
+// poison the host's CUDA context.
+constexpr uint32_t SPIN_LIMIT = 1u << 22;
+#ifdef CCSP_DEBUG_SPIN_TRAP
+#define CCSP_SPIN_GUARD(spins) do { if (++(spins) > ::ccsp::tc::SPIN_LIMIT) __trap(); } while (0)
+#else
+#define CCSP_SPIN_GUARD(spins) do { (void)(spins); } while (0)
+#endif
 
 // ---------------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -65,7 +73,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > SPIN_LIMIT) __trap();
+    CCSP_SPIN_GUARD(spins);
   }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }

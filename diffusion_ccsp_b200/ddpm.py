@@ -150,7 +150,7 @@ class GaussianDiffusion(nn.Module):
         Returns poses [n,P] on the CUDA device (and a list of T+1 tensors when return_history)."""
         assert not self.training                                                    # ddpm.py:328
         den = self.denoise_fn
-        plan = den.plan_for(batch)
+        plan = den.plan_for(batch, verify_content=True)
         dev = plan.model.device
         n, P, T = plan.n, self.dims[-1][0], self.num_timesteps
         out = torch.empty((n, P), dtype=torch.float32, device=dev)

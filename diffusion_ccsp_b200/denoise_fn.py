@@ -8,6 +8,7 @@ once into libccsp_b200's kernel layouts and calls `ccsp_denoise` through the C A
 """
 from __future__ import annotations
 
+import hashlib
 import math
 from collections import OrderedDict
 from typing import Optional
@@ -106,9 +107,7 @@ class ConstraintDiffuser(nn.Module):
         """Pack (or re-pack after an in-place weight update / load_state_dict) the CcspModel."""
         v = self._weight_versions()
         if self._abi_model is None or v != self._abi_versions or self._abi_model.math != self.math:
-            for pl in self._plans.values():
-                pl.close()
-            self._plans.clear()
+            self.drop_plans()
             if self._abi_model is not None:
                 self._abi_model.close()
             sd = {k: t for k, t in self.state_dict().items()}
@@ -129,28 +128,53 @@ class ConstraintDiffuser(nn.Module):
     @staticmethod
     def _fingerprint(batch):
         ts = (batch.x, batch.edge_index, batch.edge_attr, batch.mask)
-        return (id(batch),) + tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in ts)
+        return tuple((id(t), t.data_ptr(), t._version, tuple(t.shape)) for t in ts)
 
-    def plan_for(self, batch) -> _abi.Plan:
+    @staticmethod
+    def _content_digest(batch) -> bytes:
+        """Digest of the bytes the plan is compiled from (2 MB at config 2: ~1 ms, once per p_sample_loop)."""
+        h = hashlib.blake2b(digest_size=16)
+        for t in (batch.x, batch.edge_index, batch.edge_attr, batch.mask):
+            t = t.detach().to('cpu').contiguous()
+            h.update(str((t.dtype, tuple(t.shape))).encode())
+            h.update(t.view(torch.uint8).numpy().tobytes() if t.numel() else b'')
+        return h.digest()
+
+    def plan_for(self, batch, verify_content: bool = False) -> _abi.Plan:
         """Compile `batch` (x, edge_index, edge_attr, mask — host tensors as in the reference) once;
-        replaces the per-call uploads / per-type `where` of denoise_fn.py:466, 508, 313-339."""
+        replaces the per-call uploads / per-type `where` of denoise_fn.py:466, 508, 313-339.
+
+        Cache soundness: an entry keeps STRONG references to the four tensors it was compiled from, so
+        their ids / storage addresses cannot be recycled for another batch while the entry lives, and a hit
+        requires the very same tensor objects at the same `_version`.  Writes that bypass the version
+        counter (numpy views) are caught by the content digest, which `p_sample_loop` always checks
+        (`verify_content=True`: once per T x (1+K) evaluations); `forward` checks identity only."""
         model = self.abi_model()
         key = self._fingerprint(batch)
-        plan = self._plans.get(key)
-        if plan is None:
+        entry = self._plans.get(key)
+        if entry is not None:
+            plan, tensors, digest = entry
+            same = all(a is b for a, b in zip(tensors, (batch.x, batch.edge_index, batch.edge_attr, batch.mask)))
+            if not same or (verify_content and digest != self._content_digest(batch)):
+                plan.close()
+                del self._plans[key]
+                entry = None
+        if entry is None:
             grasp_begin = self.dims[1][1] if 'robot' in self.input_mode else 0
             plan = _abi.Plan(model, batch.x, batch.edge_index, batch.edge_attr, batch.mask,
                              pose_begin=self.dims[-1][1], grasp_begin=grasp_begin)
-            self._plans[key] = plan
+            self._plans[key] = (plan, (batch.x, batch.edge_index, batch.edge_attr, batch.mask),
+                                self._content_digest(batch))
             while len(self._plans) > self._max_plans:
                 _, old = self._plans.popitem(last=False)
-                old.close()
+                old[0].close()
         else:
             self._plans.move_to_end(key)
+            plan = entry[0]
         return plan
 
     def drop_plans(self):
-        for pl in self._plans.values():
+        for pl, _, _ in self._plans.values():
             pl.close()
         self._plans.clear()
 

@@ -26,9 +26,16 @@ DIMS = {  # train_utils.py:266-278
 
 
 def dims_for(input_mode: str, triangular: bool = False):
-    if input_mode == 'diffuse_pairwise' and triangular:
+    """Substring dispatch of train_utils.py:266-278 ('robot' / 'stability' / 'qualitative' in input_mode)."""
+    if 'robot' in input_mode:
+        return DIMS['robot_box']
+    if 'stability' in input_mode:
+        return DIMS['stability_flat']
+    if 'qualitative' in input_mode:
+        return DIMS['qualitative']
+    if triangular:
         return DIMS['diffuse_pairwise_triangular']
-    return DIMS[input_mode]
+    return DIMS['diffuse_pairwise']
 
 
 def constraint_set_for(input_mode: str):

@@ -7,15 +7,26 @@ packages that are absent from this image.  It exists so t
   * tests/golden/make_golden.py can generate golden vectors from the real reference, and
   * tests/test_oracle_vs_reference.py can pin oracle/ccsp_oracle.py against it,
 
-and it only works in the build container: /root/reference does not exist on the GPU box,
-so nothing under `-m gpu`, `smoke()` or `bench.py` may import this module.
+The sources are taken from /root/reference when it exists (the build container) and otherwise from the
+byte-identical staged copy oracle/_ref/ made by `python -m oracle.make_ref` (git-ignored, travels to the GPU
+box with the snapshot) — that is how `bench.py --impl reference` and the `cpu_baseline` leg time the
+reference's OWN implementation on the GPU box's host cores.
 Nothing in the product package (diffusion_ccsp_b200/) imports anything from oracle/.
 """
 import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("CCSP_REFERENCE_ROOT", "/root/reference")
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+REFERENCE_ROOT = os.environ.get("CCSP_REFERENCE_ROOT") or (
+    "/root/reference" if os.path.isfile("/root/reference/networks/ddpm.py") else _STAGED)
+
+
+def reference_kind() -> str:
+    """'live' (the read-only checkout), 'staged' (oracle/_ref copy) or 'absent'."""
+    if not reference_available():
+        return "absent"
+    return "staged" if os.path.abspath(REFERENCE_ROOT) == os.path.abspath(_STAGED) else "live"
 
 
 def reference_available() -> bool:

@@ -69,3 +69,42 @@ def test_state_dict_keys_match_reference_contract():
         for k, v in sd.items():
             assert gd.state_dict()[k].shape == v.shape, k
         gd.load_state_dict(sd, strict=False)
+
+
+def test_plan_cache_never_returns_a_plan_of_other_content(monkeypatch):
+    """the Trainer.evaluate pattern `batch = data.clone()` over different `data` recycles ids and
+    storage addresses; the cache must never hand back a plan compiled from other content.  CPU test with a fake Plan."""
+    import torch
+    from diffusion_ccsp_b200 import _abi, scenes, synthetic
+    from diffusion_ccsp_b200.denoise_fn import ConstraintDiffuser
+
+    class FakePlan:
+        def __init__(self, model, x, edge_index, edge_attr, mask, pose_begin, grasp_begin=0):
+            self.content = (x.clone(), edge_index.clone(), edge_attr.clone(), mask.clone())
+            self.closed = False
+
+        def close(self):
+            self.closed = True
+
+    monkeypatch.setattr(_abi, 'Plan', FakePlan)
+    den = ConstraintDiffuser(dims=synthetic.DIMS['qualitative'], input_mode='qualitative', device='cpu', verbose=False)
+    monkeypatch.setattr(den, 'abi_model', lambda: object())
+    pool = scenes.qualitative_batch(64, 4)
+    hits = 0
+    for it in range(200):
+        data = pool.select_scenes(it % 60, it % 60 + 4)
+        for _ in range(2):
+            batch = data.clone()                       # freed at the end of the iteration -> addresses get recycled
+            plan = den.plan_for(batch, verify_content=bool(it & 1))
+            assert not plan.closed
+            for a, b in zip(plan.content, (batch.x, batch.edge_index, batch.edge_attr, batch.mask)):
+                assert torch.equal(a, b), 'stale plan returned for a different batch'
+            again = den.plan_for(batch)
+            hits += again is plan
+    assert hits == 400                                  # the same live batch does hit the cache
+    # an in-place edit through a numpy view leaves _version unchanged: the digest check of p_sample_loop catches it
+    batch = pool.select_scenes(0, 4)
+    p1 = den.plan_for(batch, verify_content=True)
+    batch.x.numpy()[1, 2] += 0.25
+    p2 = den.plan_for(batch, verify_content=True)
+    assert p2 is not p1 and p1.closed and torch.equal(p2.content[0], batch.x)
