@@ -329,6 +329,29 @@ def run_ours(args):
                         frac_in_unit_box=float((free.abs() <= 1.05).float().mean()))
     value = world * B / (ms / 1e3)
 
+    # ---- N1: solved fraction of the last step's output (SolvedChecker: one launch, poses stay on the device) -------------
+    from diffusion_ccsp_b200.checker import SolvedChecker
+    checker = SolvedChecker(batch, dims, mode, dev)
+    solved = checker(out)
+    torch.cuda.synchronize(dev)
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record()
+    for _ in range(20):
+        solved, counts = checker(out, return_counts=True)
+    c1.record()
+    torch.cuda.synchronize(dev)
+    check_ms = c0.elapsed_time(c1) / 20
+    st = torch.tensor([float(solved.sum()), float(solved.numel()), float((counts[:, 0] > 0).sum()), float((counts[:, 1] > 0).sum())],
+                      device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(st)                                                 # end-of-run counters
+    solved_frac = float(st[0] / st[1])
+    solved_info = dict(solved_frac=solved_frac, solved_scenes=int(st[0]), scenes=int(st[1]), with_collisions=int(st[2]),
+                       with_missing_constraints=int(st[3]), check_ms_per_batch=check_ms,
+                       checker='k_check_solved (CUDA, 1 launch per batch; clamp + rows + SAT + 13 relations + set inclusion)',
+                       note='weights are a fixture with 74k of 9.15M parameters trained: the solved rate says nothing about the method; '
+                            'the checker itself is parity-tested bit-exactly (tests/test_gpu_checker.py)')
+
     # ---- e2e: public API with HOST buffers: plan build (H2D) + sample + D2H, wall clock ------------
     e2e = None
     if not args.no_e2e:
@@ -394,6 +417,7 @@ def run_ours(args):
                     workload_detail=dict(nodes_per_gpu=n, edges_per_gpu=E, weights='seeded init, 74k parameters (pose encoder/decoder, mlps biases) trained offline with the reference loss; 9.15 M params',
                                 noise='in-kernel Philox4x32-10', l2='explicit 256 MiB flush between steps; static term + activations (2 x %d MB) exceed L2' % (plan.edge_rows * 512 * 4 >> 20)),
                     clocks=clocks, e2e=e2e, gpu_launches=int(launches), result=result_stats,
+                    solved=solved_info, solved_scenes_per_sec=value * solved_frac,
                     roofline=roofline,
                     kernels=dict(avg_ms=dict(edge_l1=l1_ms, edge_dec=dec_ms, node=node_ms),
                                  share_of_step=dict(edge_l1=l1_ms * evals / ms, edge_dec=dec_ms * evals / ms, node=node_ms * evals / ms),

@@ -24,6 +24,7 @@ EXPORTS = [
     'ccsp_plan_create', 'ccsp_plan_destroy', 'ccsp_plan_num_nodes', 'ccsp_plan_num_edges',
     'ccsp_plan_num_edge_rows', 'ccsp_denoise', 'ccsp_sample',
     'ccsp_plan_set_timing', 'ccsp_plan_get_timing', 'ccsp_plan_h2d_bytes',
+    'ccsp_check_solved',
 ]
 
 

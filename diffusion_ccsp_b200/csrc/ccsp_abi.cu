@@ -14,6 +14,7 @@
 #include "kernels_tc.cuh"
 #include "kernels_fused2.cuh"
 #include "kernels_node_tc.cuh"
+#include "kernels_check.cuh"
 
 namespace ccsp {
 static thread_local std::string g_last_error;
@@ -809,6 +810,30 @@ int ccsp_sample(CcspPlan *p, const CcspSchedule *s, const CcspNoise *nz, float *
     }
   }
   CCSP_CUDA_TRY(cudaMemcpyAsync(out, p->x, nP * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return CCSP_OK;
+}
+
+int ccsp_check_solved(const CcspCheckDesc *d, const float *poses, uint8_t *solved, int32_t *counts, void *stream) {
+  CCSP_REQUIRE(d && poses && solved, "null argument");
+  CCSP_REQUIRE(d->kind == CCSP_WORLD_BOXES || d->kind == CCSP_WORLD_QUALITATIVE, "unknown world kind");
+  CCSP_REQUIRE(d->num_scenes >= 0 && d->x && d->scene_node_ptr && d->world_dims, "null scene arrays");
+  CCSP_REQUIRE(d->kind == CCSP_WORLD_BOXES || (d->scene_edge_ptr && d->edge_a && d->edge_b && d->edge_type), "null edge arrays");
+  CCSP_REQUIRE(d->P >= 2 && d->pose_begin >= 2 && d->pose_begin + d->P <= d->F, "rows must be [w, l, ..., pose...]");
+  CCSP_REQUIRE(d->kind == CCSP_WORLD_BOXES ? (d->F == 4 && d->pose_begin == 2 && d->P == 2)
+                                           : (d->F == 6 && d->pose_begin == 2 && d->P == 4),
+               "row layout: boxes [w,l,x,y]; qualitative [w,l,x,y,cs,sn] (data_utils.py:229-258)");
+  if (d->num_scenes == 0) return CCSP_OK;
+  int ndev = 0;
+  CCSP_CUDA_TRY(cudaGetDeviceCount(&ndev));
+  if (ndev == 0) { set_error("no CUDA device: libccsp_b200 has no CPU fallback"); return CCSP_ERR_CUDA; }
+  CheckArgs a;
+  a.kind = d->kind; a.S = d->num_scenes; a.F = d->F; a.P = d->P; a.pose_begin = d->pose_begin; a.clamp = d->clamp;
+  a.x = d->x; a.poses = poses; a.world_dims = d->world_dims;
+  a.scene_node_ptr = d->scene_node_ptr; a.scene_edge_ptr = d->scene_edge_ptr;
+  a.edge_a = d->edge_a; a.edge_b = d->edge_b; a.edge_type = d->edge_type;
+  a.solved = solved; a.counts = counts;
+  k_check_solved<<<(unsigned)((d->num_scenes + CHECK_WARPS - 1) / CHECK_WARPS), CHECK_WARPS * 32, 0, (cudaStream_t)stream>>>(a);
+  CCSP_LAUNCH_CHECK();
   return CCSP_OK;
 }
 

@@ -62,7 +62,13 @@ class Trainer(object):
     # ---- ddpm.py:558-805, sampling + bookkeeping only -------------------------------------------------
     def evaluate(self, json_name='eval', tries=(10, 0), render=False, save_log=True, run_all=False, run_only=False,
                  resume_eval=False, return_history=False, checker: Optional[Callable] = None, **kwargs):
+        """ddpm.py:558-805 — sampling, success accounting and the JSON log.  The per-graph CPU check of ddpm.py:633-713
+        (trimesh + python-fcl) runs on the GPU for the 2-D box worlds (`checker.SolvedChecker`, one launch per sample,
+        poses stay on the device); other worlds need a `checker(rows, batch) -> list[bool]` callback (none = success
+        rates are reported as None)."""
         assert not self.model.training, 'call .eval() first (ddpm.py:328)'
+        from .checker import SolvedChecker, world_kind_for
+        use_gpu_checker = checker is None and world_kind_for(self.input_mode) is not None
         log = {}
         for i, batches in self.test_datasets.items():
             count = 0
@@ -73,22 +79,29 @@ class Trainer(object):
             for data in batches:
                 base = count
                 count += data.num_graphs
+                gpu_checker = SolvedChecker(data, self.dims, self.input_mode, self.model.denoise_fn.device) if use_gpu_checker else None
                 for k in range(tries[0]):
                     batch = data.clone()                                            # ddpm.py:607
                     result = self.model.sample(batch, return_history=return_history)  # ddpm.py:612  <- the hot path
                     poses = result[0] if return_history else result
-                    poses = poses.clamp(-1, 1)                                      # ddpm.py:620
-                    rows = self.get_all_features(poses, batch)                      # ddpm.py:621
-                    if checker is not None:
-                        for j, ok in enumerate(checker(rows, batch)):
-                            if ok and (base + j) not in solved:
-                                solved.add(base + j); first_round[base + j] = k
+                    if gpu_checker is not None:
+                        flags = gpu_checker(poses).cpu().tolist()                   # clamp (ddpm.py:620) + check, on the device
+                    elif checker is not None:
+                        rows = self.get_all_features(poses.clamp(-1, 1), batch)     # ddpm.py:620-621
+                        flags = checker(rows, batch)
+                    else:
+                        flags = []
+                    for j, ok in enumerate(flags):
+                        if ok and (base + j) not in solved:
+                            solved.add(base + j); first_round[base + j] = k
                     if len(solved) == count and not run_all:
                         break
             n_samples = max(len(self.model.sample_loop_time), 1)
+            checked = use_gpu_checker or checker is not None
             log[i] = {
-                'success_rate': round(len([s for s in first_round.values() if s == 0]) / max(count, 1), 3) if checker else None,
-                'success_rate_top3': round(len(solved) / max(count, 1), 3) if checker else None,
+                'success_rate': round(len([s for s in first_round.values() if s == 0]) / max(count, 1), 3) if checked else None,
+                'success_rate_top3': round(len(solved) / max(count, 1), 3) if checked else None,
+                'success_rounds': {str(k): v for k, v in sorted(first_round.items())} if checked else None,
                 'model_ave_sample_time': sum(self.model.sample_loop_time) / n_samples / max(count, 1),   # ddpm.py:830
                 'scenes': count, 'wall_time': time.time() - t0,
             }

@@ -160,6 +160,34 @@ int ccsp_plan_get_timing(CcspPlan *p, CcspTiming *out);
 /* bytes copied host->device by ccsp_plan_create for this plan (bench.py's e2e.h2d_bytes_per_step) */
 int64_t ccsp_plan_h2d_bytes(const CcspPlan *p);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * N1: the success check behind "solved scenes / s", whole batch in one launch.
+ * Replaces: the per-graph CPU loop of Trainer.evaluate (networks/ddpm.py:620-713): clamp to [-1,1] (:620),
+ * get_all_features (:807-821), NaN skip (:644-645), render_world_from_graph (envs/data_utils.py:221-357) ->
+ * world.check_constraints_satisfied (envs/worlds.py:734-764 qualitative, :377-388 boxes) with python-fcl box-box
+ * collisions among tiles and tray walls (envs/collisions.py:58-130; exclusions worlds.py:380-388, 398) and
+ * compute_qualitative_constraints (envs/data_utils.py:427-621) + set inclusion (data_utils.py:418-424).
+ * 2-D box worlds only (4-feature rows: collisions; 6-feature rows: collisions + the 13 qualitative relations);
+ * triangle / 3-D / robot worlds need trimesh, FCL Convex or PyBullet and stay on the reference's CPU path. */
+typedef enum { CCSP_WORLD_BOXES = 0, CCSP_WORLD_QUALITATIVE = 1 } CcspWorldKind;
+
+typedef struct {
+  int32_t kind;                   /* CcspWorldKind */
+  int32_t num_scenes;             /* S */
+  int32_t F, P, pose_begin;       /* row width of x, pose width, first pose column (dims[-1][1]) */
+  int32_t clamp;                  /* 1: clamp the poses to [-1,1] first (ddpm.py:620) */
+  const float *x;                 /* dev [n,F]  batch.x (geometry columns are read from here) */
+  const int32_t *scene_node_ptr;  /* dev [S+1]  nodes of scene j = [ptr[j], ptr[j+1]), first one is the container; <= 28 tiles */
+  const int32_t *scene_edge_ptr;  /* dev [S+1]  edges grouped by scene (batch.edge_extract); ignored for CCSP_WORLD_BOXES */
+  const int32_t *edge_a, *edge_b; /* dev [E]    endpoints minus the scene's smallest edge index (ddpm.py:690-691) */
+  const int32_t *edge_type;       /* dev [E]    int(edge_attr), >= 0; ids >= 13 are skipped (data_utils.py:180-181) */
+  const float *world_dims;        /* dev [S,2]  (w_tray, l_tray) = batch.world_dims[j] */
+} CcspCheckDesc;
+
+/* poses dev [n,P] (the sampler's output, unclamped) -> solved dev u8 [S] (1 = no collision and no missing constraint);
+ * counts dev i32 [S,2] or NULL: (#collisions, #missing constraints), (-1,-1) for NaN rows.  Asynchronous on `stream`. */
+int ccsp_check_solved(const CcspCheckDesc *desc, const float *poses, uint8_t *solved, int32_t *counts, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
