@@ -182,6 +182,49 @@ class GaussianDiffusion(nn.Module):
             self.sample_loop_time.pop(0)
         return outputs
 
+    # ------------------------------------------------------------------------------------------
+    # training half (ddpm.py:353-389): loss and gradients come from ccsp_train_step (CUDA)
+    # ------------------------------------------------------------------------------------------
+    def q_sample(self, x_start, mask, t, noise=None):
+        """ddpm.py:353-361 (kept for callers; p_losses fuses it into the training kernels)."""
+        if noise is None:
+            noise = conditional_noise(x_start, mask)
+        ti = int(t.reshape(-1)[0].item()) if torch.is_tensor(t) else int(t)
+        dev = x_start.device
+        sample = self.sqrt_alphas_cumprod[ti].to(dev) * x_start + self.sqrt_one_minus_alphas_cumprod[ti].to(dev) * noise
+        sample[mask.bool()] = x_start[mask.bool()]
+        return sample
+
+    def p_losses(self, batch, t, noise=None, **kwargs):
+        """ddpm.py:363-385: q_sample with masked noise, denoiser, l1 / l2 loss — one C call (loss + every gradient); the
+        returned scalar's .backward() delivers the gradients to the nn.Parameters.  `recon=` (a [n,P] CUDA tensor, extra
+        keyword) receives the denoiser output."""
+        from .train import diffusion_loss
+        den = self.denoise_fn
+        graph = den.train_graph_for(batch)
+        dev = graph.device
+        ti = int(t.reshape(-1)[0].item()) if torch.is_tensor(t) else int(t)
+        if not 0 <= ti < self.num_timesteps:
+            raise IndexError(f't={ti} outside the schedule [0, {self.num_timesteps})')
+        if noise is None:
+            noise = torch.randn((graph.n, graph.P), dtype=torch.float32, device=dev)    # conditional_noise (ddpm.py:114-117)
+            noise[graph.mask] = 0
+        noise = noise.detach().to(dev, torch.float32).contiguous()
+        recon = kwargs.pop('recon', None)
+        loss = diffusion_loss(den, graph, ti, float(self.sqrt_alphas_cumprod[ti]), float(self.sqrt_one_minus_alphas_cumprod[ti]),
+                              noise, self.loss_type, recon)
+        if kwargs['debug']:                                                             # read unguarded in the reference (ddpm.py:374)
+            print(f'[p_losses] t={ti} loss={float(loss):.6f}')
+        return loss
+
     def forward(self, batch, **kwargs):
-        raise NotImplementedError('training loss (q_sample/p_losses, ddpm.py:353-389) is the "next" row N2 '
-                                  'of SURVEY.md §8f and is not part of the sampling path')
+        """ddpm.py:387-389: ONE random timestep per batch."""
+        t = torch.randint(0, self.num_timesteps, (1,)).long()
+        return self.p_losses(batch, t, **kwargs)
+
+
+def conditional_noise(x, mask):
+    """ddpm.py:114-117."""
+    noise = torch.randn_like(x)
+    noise[mask.bool()] = 0
+    return noise

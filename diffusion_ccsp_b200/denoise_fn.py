@@ -94,14 +94,20 @@ class ConstraintDiffuser(nn.Module):
 
         self._abi_model: Optional[_abi.Model] = None
         self._abi_versions = None
-        self._plans = OrderedDict()          # batch fingerprint -> _abi.Plan (small LRU)
+        self._plans = OrderedDict()          # batch fingerprint -> (_abi.Plan, tensors, digest) (small LRU)
         self._max_plans = 4
+        self._train_graphs = OrderedDict()   # same keying, for the training step (train.TrainGraph)
+        self._dirty = 0
 
     # ------------------------------------------------------------------------------------------
     # weights -> CcspModel
     # ------------------------------------------------------------------------------------------
     def _weight_versions(self):
-        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+        return (self._dirty,) + tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def mark_weights_dirty(self):
+        """Call after the parameters were updated through raw device pointers (train.Adam): the next sampling call re-packs them."""
+        self._dirty += 1
 
     def abi_model(self) -> _abi.Model:
         """Pack (or re-pack after an in-place weight update / load_state_dict) the CcspModel."""
@@ -150,33 +156,55 @@ class ConstraintDiffuser(nn.Module):
         counter (numpy views) are caught by the content digest, which `p_sample_loop` always checks
         (`verify_content=True`: once per T x (1+K) evaluations); `forward` checks identity only."""
         model = self.abi_model()
+
+        def build():
+            grasp_begin = self.dims[1][1] if 'robot' in self.input_mode else 0
+            return _abi.Plan(model, batch.x, batch.edge_index, batch.edge_attr, batch.mask,
+                             pose_begin=self.dims[-1][1], grasp_begin=grasp_begin)
+        return self._cached(self._plans, self._max_plans, batch, build, verify_content)
+
+    def _cached(self, store, cap, batch, build, verify_content):
         key = self._fingerprint(batch)
-        entry = self._plans.get(key)
+        tensors = (batch.x, batch.edge_index, batch.edge_attr, batch.mask)
+        entry = store.get(key)
         if entry is not None:
-            plan, tensors, digest = entry
-            same = all(a is b for a, b in zip(tensors, (batch.x, batch.edge_index, batch.edge_attr, batch.mask)))
+            obj, held, digest = entry
+            same = all(a is b for a, b in zip(held, tensors))
             if not same or (verify_content and digest != self._content_digest(batch)):
-                plan.close()
-                del self._plans[key]
+                obj.close()
+                del store[key]
                 entry = None
         if entry is None:
-            grasp_begin = self.dims[1][1] if 'robot' in self.input_mode else 0
-            plan = _abi.Plan(model, batch.x, batch.edge_index, batch.edge_attr, batch.mask,
-                             pose_begin=self.dims[-1][1], grasp_begin=grasp_begin)
-            self._plans[key] = (plan, (batch.x, batch.edge_index, batch.edge_attr, batch.mask),
-                                self._content_digest(batch))
-            while len(self._plans) > self._max_plans:
-                _, old = self._plans.popitem(last=False)
+            obj = build()
+            store[key] = (obj, tensors, self._content_digest(batch))
+            while len(store) > cap:
+                _, old = store.popitem(last=False)
                 old[0].close()
         else:
-            self._plans.move_to_end(key)
-            plan = entry[0]
-        return plan
+            store.move_to_end(key)
+            obj = entry[0]
+        return obj
+
+    def cuda_device(self) -> torch.device:
+        """the device the kernels run on: where the parameters live if that is a CUDA device, else `self.device`"""
+        p = next(self.parameters())
+        if p.is_cuda:
+            return p.device
+        if self.device.type == 'cuda':
+            return self.device if self.device.index is not None else torch.device('cuda', torch.cuda.current_device())
+        raise _abi.CcspError('no CUDA device configured for this model (device=%r): there is no CPU fallback' % (self.device,))
+
+    def train_graph_for(self, batch):
+        """Compile `batch` for the training step (train.TrainGraph); cached like the sampling plans."""
+        from .train import TrainGraph
+        dev = self.cuda_device()
+        return self._cached(self._train_graphs, 2, batch, lambda: TrainGraph(self, batch, dev), True)
 
     def drop_plans(self):
-        for pl, _, _ in self._plans.values():
-            pl.close()
-        self._plans.clear()
+        for store in (self._plans, self._train_graphs):
+            for obj, _, _ in store.values():
+                obj.close()
+            store.clear()
 
     # ------------------------------------------------------------------------------------------
     def forward(self, poses_in, batch, t, verbose=False, debug=False, tag='EBM', eval=False):

@@ -127,6 +127,25 @@ def take_scenes(batch: SceneBatch, ids: Sequence[int]) -> SceneBatch:
     return collate([batch.select_scenes(int(i), int(i) + 1) for i in ids])
 
 
+class SceneLoader:
+    """Minimal stand-in for `torch_geometric.loader.DataLoader(dataset, batch_size, shuffle)` (ddpm.py:443-449) over a pool of
+    scenes: yields collated SceneBatch objects of `batch_size` scenes (the last one may be smaller), reshuffled every epoch."""
+
+    def __init__(self, pool, batch_size: int, shuffle: bool = False, seed: int = 0):
+        self.scenes = ([pool.select_scenes(i, i + 1) for i in range(pool.num_graphs)] if isinstance(pool, SceneBatch)
+                       else list(pool))
+        self.batch_size, self.shuffle = int(batch_size), shuffle
+        self._rng = np.random.default_rng(seed)
+
+    def __len__(self):
+        return (len(self.scenes) + self.batch_size - 1) // self.batch_size
+
+    def __iter__(self):
+        order = self._rng.permutation(len(self.scenes)) if self.shuffle else np.arange(len(self.scenes))
+        for i in range(0, len(order), self.batch_size):
+            yield collate([self.scenes[j] for j in order[i:i + self.batch_size]])
+
+
 # =====================================================================================
 # synthetic generators
 # =====================================================================================

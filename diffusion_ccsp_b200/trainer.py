@@ -23,23 +23,35 @@ import torch
 
 from .ddpm import GaussianDiffusion
 from .denoise_fn import ConstraintDiffuser
-from .scenes import SceneBatch
+from .scenes import SceneBatch, SceneLoader
 from .synthetic import dims_for
 
 
 class Trainer(object):
     def __init__(self, denoise_fn: GaussianDiffusion, train_dataset=None, test_datasets: Optional[Dict] = None,
-                 render_dir: str = './renders', *, results_folder: str = './results', EBM=False, eval_only=True,
-                 input_mode=None, **kwargs):
+                 render_dir: str = './renders', *, train_batch_size=32, train_lr=2e-3, train_num_steps=100000,
+                 gradient_accumulate_every=2, save_and_sample_every=10000, results_folder: str = './results', EBM=False,
+                 eval_only=True, input_mode=None, loader_seed=0, **kwargs):
+        """ddpm.py:395-490.  `train_dataset`: a SceneBatch pool (or list of single-scene SceneBatch objects) standing in for the
+        GraphDataset; `test_datasets`: {n_objects: iterable of SceneBatch}.  EMA is disabled in the reference (ema_model = None,
+        ddpm.py:426) and therefore absent here."""
         self.model = denoise_fn
         self.dims = denoise_fn.dims
         self.input_mode = denoise_fn.input_mode
         self.EBM = EBM
+        self.batch_size = train_batch_size
+        self.gradient_accumulate_every = gradient_accumulate_every
+        self.train_num_steps = train_num_steps
+        self.save_and_sample_every = save_and_sample_every
+        self.train_dl = SceneLoader(train_dataset, train_batch_size, shuffle=True, seed=loader_seed) if train_dataset is not None else None
         self.test_datasets = test_datasets or {}      # {n_objects: iterable of SceneBatch}
         self.eval_kwargs = dict(tries=(10, 0))
         self.render_dir = render_dir
         self.results_folder = Path(results_folder)
+        self.train_lr = train_lr
+        self.opt = None                                # train.Adam, created on first use (needs the parameters on the GPU)
         self.step = 0
+        self.loss_log = []
 
     # ---- checkpoints (ddpm.py:496-514) --------------------------------------------------------------
     def save(self, milestone):
@@ -56,8 +68,50 @@ class Trainer(object):
         return torch.cat([batch.x[:, :self.dims[-1][1]].cpu(), all_features.detach().cpu(),
                           batch.x[:, self.dims[-1][2]:].cpu()], dim=1)
 
-    def train(self):
-        raise NotImplementedError('training is the "next" row N2 of SURVEY.md §8f')
+    def _optimizer(self):
+        if self.opt is None:
+            from .train import Adam
+            den = self.model.denoise_fn
+            den.to(den.cuda_device())
+            self.opt = Adam(self.model.parameters(), lr=self.train_lr, on_step=den.mark_weights_dirty)   # ddpm.py:466
+        return self.opt
+
+    def train(self, log_every: int = 1000, evaluate: bool = True):
+        """ddpm.py:519-556: gradient accumulation, Adam step, periodic save + evaluate.  The loss and every gradient come
+        from the CUDA training step (`self.model(data, debug=False, tag='EBM')` -> ccsp_train_step)."""
+        if self.train_dl is None:
+            raise ValueError('Trainer.train needs a train_dataset')
+        opt = self._optimizer()
+        self.model.train()
+        dl_iter = iter(self.train_dl)
+        window = []
+        while self.step < self.train_num_steps:
+            for _ in range(self.gradient_accumulate_every):
+                try:
+                    data = next(dl_iter)
+                except StopIteration:
+                    dl_iter = iter(self.train_dl)
+                    data = next(dl_iter)
+                loss = self.model(data, debug=False, tag='EBM')
+                window.append(loss.detach())
+                (loss / self.gradient_accumulate_every).backward()                  # ddpm.py:534
+            if (self.step + 1) % log_every == 0:
+                mean = float(torch.stack(window).mean())
+                self.loss_log.append((self.step, mean))
+                print(f"Step: {self.step} | lr: {opt.param_groups[0]['lr']}\tloss={mean:.6f}")
+                window = []
+            opt.step()
+            opt.zero_grad()
+            if self.step % self.save_and_sample_every == (self.save_and_sample_every - 1):
+                milestone = self.step // self.save_and_sample_every
+                self.save(milestone)
+                if evaluate and self.test_datasets:
+                    self.model.eval()
+                    self.evaluate(milestone, **self.eval_kwargs)
+                    self.model.train()
+            self.step += 1
+        self.model.eval()
+        print('training completed')
 
     # ---- ddpm.py:558-805, sampling + bookkeeping only -------------------------------------------------
     def evaluate(self, json_name='eval', tries=(10, 0), render=False, save_log=True, run_all=False, run_only=False,
@@ -113,15 +167,20 @@ class Trainer(object):
 
 
 def create_trainer(input_mode='qualitative', timesteps=1000, EBM='ULA', samples_per_step=10, step_sizes='2*self.betas',
-                   hidden_dim=256, normalize=True, train_task='', test_datasets=None, results_folder='./logs/run',
-                   render_dir='./renders/run', device='cuda', math='bf16x3', **kwargs) -> Trainer:
-    """train_utils.py:185-313 reduced to the model/diffusion/trainer factory (no datasets, no wandb)."""
+                   hidden_dim=256, normalize=True, train_task='', train_dataset=None, test_datasets=None, train_num_steps=300000,
+                   train_batch_size=128, train_lr=5e-4, results_folder='./logs/run', render_dir='./renders/run', device='cuda',
+                   math='bf16x3', loss_type='l2', **kwargs) -> Trainer:
+    """train_utils.py:185-313 reduced to the model / diffusion / trainer factory (datasets are handed in; no wandb).
+    Training configuration as at train_utils.py:216-219, 299-313: batch 128, lr 5e-4, gradient_accumulate_every=1."""
     dims = dims_for(input_mode, 'Triangular' in train_task)
     denoise_fn = ConstraintDiffuser(dims=dims, hidden_dim=hidden_dim, EBM=EBM, input_mode=input_mode, normalize=normalize,
                                     energy_wrapper=False, device=device, verbose=False, math=math)
-    diffusion = GaussianDiffusion(denoise_fn, timesteps=timesteps, EBM=EBM, samples_per_step=samples_per_step,
+    diffusion = GaussianDiffusion(denoise_fn, timesteps=timesteps, loss_type=loss_type, EBM=EBM, samples_per_step=samples_per_step,
                                   step_sizes=step_sizes).eval()
-    return Trainer(diffusion, None, test_datasets, render_dir, results_folder=results_folder, EBM=EBM, input_mode=input_mode)
+    return Trainer(diffusion, train_dataset, test_datasets, render_dir, train_batch_size=train_batch_size, train_lr=train_lr,
+                   train_num_steps=train_num_steps, gradient_accumulate_every=1,
+                   save_and_sample_every=kwargs.pop('save_and_sample_every', 10000),
+                   results_folder=results_folder, EBM=EBM, input_mode=input_mode, **kwargs)
 
 
 def load_trainer(run_id, milestone, logs_dir='./logs', **kwargs) -> Trainer:

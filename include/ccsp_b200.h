@@ -188,6 +188,57 @@ typedef struct {
  * counts dev i32 [S,2] or NULL: (#collisions, #missing constraints), (-1,-1) for NaN rows.  Asynchronous on `stream`. */
 int ccsp_check_solved(const CcspCheckDesc *desc, const float *poses, uint8_t *solved, int32_t *counts, void *stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * N2: the training step.  The reference computes loss = GaussianDiffusion(batch, debug=False, tag='EBM')
+ * (networks/ddpm.py:387-389 -> p_losses :363-385 -> q_sample :353-361 with masked noise :114-117 -> ConstraintDiffuser.forward
+ * denoise_fn.py:453-537 -> F.mse_loss :383) and gets the gradients from autograd (loss.backward(), ddpm.py:136-142, 533-534),
+ * then torch.optim.Adam (ddpm.py:466, 542).  Here one call computes the loss and d(grad_scale * loss)/d(parameter) for every
+ * parameter with hand-written FP32 kernels (fixed summation order: bit-reproducible). */
+typedef struct CcspTrainGraph CcspTrainGraph;
+
+typedef struct {
+  int32_t hidden_dim;      /* must equal CCSP_HIDDEN_DIM */
+  int32_t geom_dim, pose_dim, grasp_dim, num_types, normalize;   /* as in CcspModelDesc */
+  int32_t row_width;       /* F: columns of batch.x */
+  int32_t pose_begin;      /* dims[-1][1] */
+  int32_t grasp_begin;     /* dims[1][1] in robot mode */
+} CcspTrainDims;
+
+/* Parameters (or their gradients) of ConstraintDiffuser as DEVICE pointers in the reference's nn.Linear layouts
+ * ([out_features, in_features] row-major, see CcspModelDesc); mlp_w / mlp_b are HOST arrays of num_types device pointers. */
+typedef struct {
+  float *geom_w0, *geom_b0, *geom_w2, *geom_b2;
+  float *grasp_w0, *grasp_b0, *grasp_w2, *grasp_b2;    /* NULL unless robot mode */
+  float *pose_w0, *pose_b0, *pose_w2, *pose_b2;
+  float *dec_w0, *dec_b0, *dec_w2, *dec_b2;
+  float *time_w1, *time_b1, *time_w3, *time_b3;
+  float *const *mlp_w;
+  float *const *mlp_b;
+} CcspParams;
+
+/* Replaces: the per-call graph handling of ConstraintDiffuser.forward for a training batch (same inputs as ccsp_plan_create:
+ * HOST x [n,F] f32, edge_index [2,E] i64, edge_attr [E] f32, mask [n] i8); allocates the activation buffers. Synchronous. */
+int ccsp_train_graph_create(const CcspTrainDims *dims, const float *x, int64_t n, const int64_t *edge_index,
+                            const float *edge_attr, const int8_t *mask, int64_t E, void *stream, CcspTrainGraph **out);
+void ccsp_train_graph_destroy(CcspTrainGraph *g);
+/* edges of constraint type c in the batch; a type without edges is not part of the reference's autograd graph, so its
+ * mlps[c] gradients are None there (denoise_fn.py:514-515) — here they come back as zeros */
+int64_t ccsp_train_graph_num_edges_of_type(const CcspTrainGraph *g, int32_t c);
+
+/* Replaces: p_losses + loss.backward().  t = the batch's timestep (ddpm.py:388 draws ONE per batch), the two schedule scalars
+ * are sqrt_alphas_cumprod[t] / sqrt_one_minus_alphas_cumprod[t] (ddpm.py:356-357), noise dev [n,P] = `all_noise` of p_losses, used as
+ * given (conditional_noise zeroes the rows of pinned nodes, ddpm.py:114-117: the caller does that when it draws the noise).  loss_l1: 0 = 'l2' (mse), 1 = 'l1' (ddpm.py:380-383).
+ * Writes *loss_out (dev scalar, the unscaled loss) and OVERWRITES every buffer of `grads` with d(grad_scale * loss)/d(param);
+ * out_recon (dev [n,P], nullable) receives the denoiser output.  Asynchronous on `stream`. */
+int ccsp_train_step(CcspTrainGraph *g, const CcspParams *weights, const CcspParams *grads, int32_t t,
+                    float sqrt_alphas_cumprod_t, float sqrt_one_minus_alphas_cumprod_t, const float *noise,
+                    int32_t loss_l1, float grad_scale, float *loss_out, float *out_recon, void *stream);
+
+/* Replaces: torch.optim.Adam.step for one flat tensor (defaults: no weight decay, no amsgrad; ddpm.py:466): step >= 1 is the
+ * 1-based update count.  All pointers dev [count].  Asynchronous on `stream`. */
+int ccsp_adam_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t count, int32_t step,
+                   float lr, float beta1, float beta2, float eps, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

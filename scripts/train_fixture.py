@@ -1,0 +1,78 @@
+#!/usr/bin/env python
+"""Train a qualitative-world checkpoint on the GPU with the repo's OWN training step (no reference code involved), then
+sample the held-out pool and report the solved rate from the GPU checker.
+
+    python scripts/train_fixture.py --steps 3000 --out gpurun_out/ckpt
+
+Training pool: the committed RandomSplitQualitativeWorld fixture scenes (N = 3, 4, 6 and the SECOND half of the N = 8 pool);
+evaluation: the FIRST 256 scenes of the N = 8 pool (disjoint).  Prints a JSON line with the loss curve and the solved rates.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from diffusion_ccsp_b200 import scenes, synthetic  # noqa: E402
+from diffusion_ccsp_b200.checker import SolvedChecker  # noqa: E402
+from diffusion_ccsp_b200.trainer import create_trainer  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--steps', type=int, default=3000)
+    ap.add_argument('--batch', type=int, default=128)
+    ap.add_argument('--timesteps', type=int, default=1000)
+    ap.add_argument('--eval-every', type=int, default=1000)
+    ap.add_argument('--eval-scenes', type=int, default=256)
+    ap.add_argument('--out', default='gpurun_out/ckpt')
+    ap.add_argument('--seed', type=int, default=0)
+    a = ap.parse_args()
+    torch.manual_seed(a.seed)
+    pool8 = scenes.qualitative_batch(1024, 8)
+    train_pool = scenes.collate([pool8.select_scenes(512, 1024), scenes.qualitative_batch(64, 4), scenes.qualitative_batch(16, 6),
+                                 scenes.qualitative_batch(16, 3)])
+    eval_batch = pool8.select_scenes(0, a.eval_scenes)
+    dims = synthetic.DIMS['qualitative']
+    sd = synthetic.make_state_dict(dims, 'qualitative', seed=0)
+    tr = create_trainer('qualitative', timesteps=a.timesteps, EBM='ULA', train_dataset=train_pool, train_num_steps=0,
+                        train_batch_size=a.batch, results_folder=a.out, render_dir=a.out, device='cuda')
+    tr.model.load_state_dict(sd, strict=False)
+    checker = SolvedChecker(eval_batch, dims, 'qualitative', 'cuda')
+    log = dict(steps=[], loss=[], solved=[], train_s=[], config=vars(a))
+    t_train = 0.0
+    done = 0
+    while done < a.steps:
+        n = min(a.eval_every, a.steps - done)
+        tr.train_num_steps = done + n
+        torch.cuda.synchronize(); t0 = time.time()
+        tr.train(log_every=max(n // 4, 1), evaluate=False)
+        torch.cuda.synchronize(); t_train += time.time() - t0
+        done += n
+        tr.model.eval()
+        poses = tr.model.sample(eval_batch, seed=1)
+        solved, counts = checker(poses, return_counts=True)
+        frac = float(solved.float().mean())
+        free = poses[~eval_batch.mask.bool().cuda()]
+        print(f'[fixture] step {done}: loss {tr.loss_log[-1][1]:.5f}  solved {frac:.3f}  collisions {(counts[:, 0] > 0).float().mean():.3f} '
+              f'missing {(counts[:, 1] > 0).float().mean():.3f}  max|x| {float(free.abs().max()):.2f}  train {t_train:.1f}s', flush=True)
+        log['steps'].append(done); log['loss'].append(tr.loss_log[-1][1]); log['solved'].append(frac); log['train_s'].append(t_train)
+    os.makedirs(a.out, exist_ok=True)
+    tr.step = done
+    tr.save('fixture')
+    half = {k: v.half() for k, v in tr.model.state_dict().items() if k.startswith('denoise_fn.')}
+    torch.save(half, os.path.join(a.out, 'denoise_fn_fp16.pt'))
+    log['loss_log'] = tr.loss_log
+    log['ms_per_step'] = t_train / max(done, 1) * 1e3
+    with open(os.path.join(a.out, 'train_log.json'), 'w') as f:
+        json.dump(log, f)
+    print(json.dumps(dict(steps=done, final_loss=log['loss'][-1], solved=log['solved'], ms_per_train_step=log['ms_per_step'])))
+
+
+if __name__ == '__main__':
+    main()
