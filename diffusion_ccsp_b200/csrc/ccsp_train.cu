@@ -21,6 +21,36 @@ using namespace ccsp::train;
     }                                                        \
   } while (0)
 
+namespace {
+// Device blocks of destroyed training graphs, reused by the next one: a training loop compiles a new batch every step and
+// cudaMalloc / cudaFree of ~40 blocks per step (cudaFree synchronises the device) would dominate a few-millisecond step.
+struct TrainBlockCache {
+  struct Blk { void *p; size_t bytes; int device; };
+  std::vector<Blk> blocks;
+  size_t bytes = 0;
+  static constexpr size_t kCap = (size_t)6 << 30;
+  void *take(size_t need, int device, size_t *actual) {
+    int best = -1;
+    for (int i = 0; i < (int)blocks.size(); ++i)
+      if (blocks[i].device == device && blocks[i].bytes >= need && blocks[i].bytes <= 2 * need + ((size_t)1 << 16) &&
+          (best < 0 || blocks[i].bytes < blocks[best].bytes))
+        best = i;
+    if (best < 0) return nullptr;
+    void *p = blocks[best].p;
+    *actual = blocks[best].bytes;
+    bytes -= blocks[best].bytes;
+    blocks.erase(blocks.begin() + best);
+    return p;
+  }
+  void give(void *p, size_t sz, int device) {
+    if (bytes + sz > kCap) { cudaFree(p); return; }
+    blocks.push_back(Blk{p, sz, device});
+    bytes += sz;
+  }
+};
+thread_local TrainBlockCache g_train_cache;     // one per host thread / rank, like the handles themselves
+}  // namespace
+
 struct CcspTrainGraph {
   int device = 0;
   int G = 0, P = 0, Gr = 0, C = 0, F = 0, normalize = 1, pose_begin = 0, grasp_begin = 0;
@@ -28,7 +58,7 @@ struct CcspTrainGraph {
   int nseg = 4, Kseg = 1024, Kin = 1280;
   int start[MAX_TYPES + 1] = {0};        // padded row range per type
   int rows_of_type[MAX_TYPES] = {0};     // real edges per type
-  std::vector<void *> blocks;
+  std::vector<std::pair<void *, size_t>> blocks;
   // graph
   float *x = nullptr, *x0 = nullptr, *xtail = nullptr, *freqs = nullptr;
   int *src_i = nullptr, *src_j = nullptr, *tile_type = nullptr, *node_ptr = nullptr, *node_src = nullptr, *type_rows = nullptr;
@@ -38,24 +68,27 @@ struct CcspTrainGraph {
   float *enc_z1[3] = {}, *enc_a1[3] = {}, *enc_z2[3] = {}, *enc_e[3] = {}, *enc_dz2[3] = {}, *enc_dz1[3] = {};   // geom, pose, grasp
   float *emb = nullptr, *tz1 = nullptr, *ta1 = nullptr, *temb = nullptr, *dtemb = nullptr, *bias = nullptr, *dbias = nullptr;
   float *Z = nullptr, *H = nullptr, *D1 = nullptr, *A1 = nullptr, *O = nullptr, *out = nullptr, *err = nullptr;
-  float *dOut = nullptr, *dO = nullptr, *dD1 = nullptr, *dZ = nullptr, *dIn = nullptr, *part = nullptr;
+  float *dOut = nullptr, *dO = nullptr, *dD1 = nullptr, *dZ = nullptr, *dIn = nullptr, *part = nullptr, *colpart = nullptr, *dtemb_part = nullptr;
   size_t part_floats = 0;
 
   template <typename T>
   cudaError_t alloc(T **p, size_t count) {
-    void *q = nullptr;
-    cudaError_t e = cudaMalloc(&q, (count ? count : 1) * sizeof(T));
-    if (e == cudaSuccess) { blocks.push_back(q); *p = (T *)q; }
+    size_t bytes = ((count ? count : 1) * sizeof(T) + 255) & ~(size_t)255, actual = 0;
+    void *q = g_train_cache.take(bytes, device, &actual);
+    cudaError_t e = cudaSuccess;
+    if (!q) { actual = bytes; e = cudaMalloc(&q, bytes); }
+    if (e == cudaSuccess) { blocks.emplace_back(q, actual); *p = (T *)q; }
     return e;
   }
   template <typename T>
   cudaError_t upload(T **p, const std::vector<T> &h) {
     cudaError_t e = alloc(p, h.size());
     if (e != cudaSuccess || h.empty()) return e;
-    return cudaMemcpy(*p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
+    return cudaMemcpyAsync(*p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, upload_stream);
   }
-  void free_all() {
-    for (void *b : blocks) cudaFree(b);
+  cudaStream_t upload_stream = nullptr;
+  void free_all() {          // the caller has synchronised the device: the blocks may be reused at once
+    for (auto &b : blocks) g_train_cache.give(b.first, b.second, device);
     blocks.clear();
   }
 };
@@ -87,13 +120,18 @@ int weight_grad(CcspTrainGraph *g, const float *dY, const float *X, int M, int N
   return CCSP_OK;
 }
 
-int col_sum(const float *Mx, int ld, int cols, int64_t r0, int64_t r1, float *out, cudaStream_t st) {
-  ColSumArgs a;
-  std::memset(&a, 0, sizeof(a));
-  a.M = Mx; a.ld = ld; a.cols = cols; a.start[0] = (int)r0; a.start[1] = (int)r1; a.out = out;
-  k_colsum<<<dim3((unsigned)((cols + 31) / 32), 1), 256, 0, st>>>(a);
+int col_sums(ColSumArgs &a, cudaStream_t st) {
+  k_colsum<<<dim3((unsigned)((a.cols + 31) / 32), (unsigned)a.groups, COLSUM_SLICES), 256, 0, st>>>(a);
+  CCSP_LAUNCH_CHECK();
+  k_colsum_finish<<<(unsigned)((a.groups * a.cols + 255) / 256), 256, 0, st>>>(a);
   CCSP_LAUNCH_CHECK();
   return CCSP_OK;
+}
+int col_sum(CcspTrainGraph *g, const float *Mx, int ld, int cols, int64_t r0, int64_t r1, float *out, cudaStream_t st) {
+  ColSumArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.M = Mx; a.ld = ld; a.cols = cols; a.groups = 1; a.start[0] = (int)r0; a.start[1] = (int)r1; a.out = out; a.part = g->colpart;
+  return col_sums(a, st);
 }
 
 struct EncPtrs { const float *w0, *b0, *w2, *b2; };
@@ -135,6 +173,8 @@ int ccsp_train_graph_create(const CcspTrainDims *d, const float *x, int64_t n, c
     }
   }
   CcspTrainGraph *g = new CcspTrainGraph();
+  if (cudaGetDevice(&g->device) != cudaSuccess) { delete g; set_error("cudaGetDevice failed"); return CCSP_ERR_CUDA; }
+  g->upload_stream = st;
   std::vector<int> tile_type;
   for (int c = 0; c < C; ++c) {
     const int64_t tiles = (cnt[c] + TILE_ROWS - 1) / TILE_ROWS;
@@ -185,7 +225,6 @@ int ccsp_train_graph_create(const CcspTrainDims *d, const float *x, int64_t n, c
   }
   std::vector<int> type_rows(g->rows_of_type, g->rows_of_type + MAX_TYPES);
 
-  CCSP_CUDA_TRY(cudaGetDevice(&g->device));
   g->G = d->geom_dim; g->P = P; g->Gr = d->grasp_dim; g->C = C; g->F = F; g->normalize = d->normalize ? 1 : 0;
   g->pose_begin = d->pose_begin; g->grasp_begin = d->grasp_begin;
   g->n = n; g->E = E; g->Epad = Epad;
@@ -225,6 +264,8 @@ int ccsp_train_graph_create(const CcspTrainDims *d, const float *x, int64_t n, c
   G_TRY(g->alloc(&g->dIn, Ep * g->Kseg));
   g->part_floats = (size_t)64 * CCSP_HH * CCSP_H;
   G_TRY(g->alloc(&g->part, g->part_floats));
+  G_TRY(g->alloc(&g->colpart, (size_t)COLSUM_SLICES * MAX_TYPES * CCSP_H2));
+  G_TRY(g->alloc(&g->dtemb_part, (size_t)MAX_TYPES * 8 * CCSP_H));
   G_TRY(cudaStreamSynchronize(st));
 #undef G_TRY
   *out = g;
@@ -289,7 +330,11 @@ int ccsp_train_step(CcspTrainGraph *g, const CcspParams *w, const CcspParams *dw
     p.M_ = n; p.N_ = CCSP_H; p.K_ = CCSP_HH;
     if ((rc = launch_gemm(p, n, CCSP_H, 1, st))) return rc;
   }
-  k_time_fwd<<<1, 256, 0, st>>>(t, w->time_w1, w->time_b1, w->time_w3, w->time_b3, g->emb, g->tz1, g->ta1, g->temb);
+  k_time_gemv<0><<<4 * CCSP_H / 8, 256, CCSP_H * sizeof(float), st>>>(t, g->freqs, nullptr, w->time_w1, w->time_b1, 4 * CCSP_H, CCSP_H,
+                                                                     g->emb, g->tz1, g->ta1);
+  CCSP_LAUNCH_CHECK();
+  k_time_gemv<1><<<CCSP_H / 8, 256, 4 * CCSP_H * sizeof(float), st>>>(t, g->freqs, g->ta1, w->time_w3, w->time_b3, CCSP_H, 4 * CCSP_H,
+                                                                     nullptr, nullptr, g->temb);
   CCSP_LAUNCH_CHECK();
   k_time_bias_fwd<<<C, 512, 0, st>>>(W, B, g->Kin, g->Kseg, g->temb, g->bias);
   CCSP_LAUNCH_CHECK();
@@ -328,11 +373,11 @@ int ccsp_train_step(CcspTrainGraph *g, const CcspParams *w, const CcspParams *dw
     k_dO<<<(rows2 * P + 255) / 256, 256, 0, st>>>(g->dOut, g->src_i, g->src_j, n, rows2, P, g->dO);
     CCSP_LAUNCH_CHECK();
     if ((rc = weight_grad(g, g->dO, g->A1, P, CCSP_HH, rows2, dw->dec_w2, st))) return rc;
-    if ((rc = col_sum(g->dO, P, P, 0, rows2, dw->dec_b2, st))) return rc;
+    if ((rc = col_sum(g, g->dO, P, P, 0, rows2, dw->dec_b2, st))) return rc;
     k_dD1<<<(unsigned)(((size_t)rows2 * CCSP_HH + 255) / 256), 256, 0, st>>>(g->dO, w->dec_w2, g->D1, rows2, P, g->dD1);
     CCSP_LAUNCH_CHECK();
     if ((rc = weight_grad(g, g->dD1, g->H, CCSP_HH, CCSP_H, rows2, dw->dec_w0, st))) return rc;
-    if ((rc = col_sum(g->dD1, CCSP_HH, CCSP_HH, 0, rows2, dw->dec_b0, st))) return rc;
+    if ((rc = col_sum(g, g->dD1, CCSP_HH, CCSP_HH, 0, rows2, dw->dec_b0, st))) return rc;
     {
       LinearBwdInput p;
       p.dY = g->dD1; p.W = w->dec_w0; p.Zx = g->Z; p.dX = g->dZ; p.M_ = rows2; p.N_ = CCSP_H; p.K_ = CCSP_HH;
@@ -341,10 +386,9 @@ int ccsp_train_step(CcspTrainGraph *g, const CcspParams *w, const CcspParams *dw
     {  // db_c and, through them, the time columns
       ColSumArgs a;
       std::memset(&a, 0, sizeof(a));
-      a.M = g->dZ; a.ld = CCSP_H2; a.cols = CCSP_H2; a.out = g->dbias;
+      a.M = g->dZ; a.ld = CCSP_H2; a.cols = CCSP_H2; a.groups = C; a.out = g->dbias; a.part = g->colpart;
       for (int c = 0; c <= MAX_TYPES; ++c) a.start[c] = g->start[c];
-      k_colsum<<<dim3(CCSP_H2 / 32, C), 256, 0, st>>>(a);
-      CCSP_LAUNCH_CHECK();
+      if ((rc = col_sums(a, st))) return rc;
       for (int c = 0; c < C; ++c)
         CCSP_CUDA_TRY(cudaMemcpyAsync(dB.p[c], g->dbias + (size_t)c * CCSP_H2, CCSP_H2 * sizeof(float), cudaMemcpyDeviceToDevice, st));
     }
@@ -371,9 +415,10 @@ int ccsp_train_step(CcspTrainGraph *g, const CcspParams *w, const CcspParams *dw
       CCSP_CUDA_TRY(cudaMemsetAsync(dB.p[c], 0, (size_t)CCSP_H2 * sizeof(float), st));
     }
   }
-  k_time_cols_bwd<<<C + 1, 256, 0, st>>>(W, dW, C, g->Kin, g->Kseg, g->temb, g->dbias, g->type_rows, g->dtemb);
+  k_time_cols_bwd<<<dim3(C, 8), 256, 0, st>>>(W, dW, g->Kin, g->Kseg, g->temb, g->dbias, g->type_rows, g->dtemb_part);
   CCSP_LAUNCH_CHECK();
-  k_time_bwd<<<1, 256, 0, st>>>(g->dtemb, g->emb, g->tz1, g->ta1, w->time_w3, dw->time_w1, dw->time_b1, dw->time_w3, dw->time_b3);
+  k_time_bwd<<<4 * CCSP_H / 16, 256, 0, st>>>(g->dtemb_part, C * 8, g->emb, g->tz1, g->ta1, w->time_w3, dw->time_w1, dw->time_b1, dw->time_w3,
+                                               dw->time_b3);
   CCSP_LAUNCH_CHECK();
   {
     NodeBwdArgs a;
@@ -389,7 +434,7 @@ int ccsp_train_step(CcspTrainGraph *g, const CcspParams *w, const CcspParams *dw
   }
   for (int tb = 0; tb < ntab; ++tb) {
     if ((rc = weight_grad(g, g->enc_dz2[tb], g->enc_a1[tb], CCSP_H, CCSP_HH, n, eg[tb].w2, st))) return rc;
-    if ((rc = col_sum(g->enc_dz2[tb], CCSP_H, CCSP_H, 0, n, eg[tb].b2, st))) return rc;
+    if ((rc = col_sum(g, g->enc_dz2[tb], CCSP_H, CCSP_H, 0, n, eg[tb].b2, st))) return rc;
     LinearBwdInput p;
     p.dY = g->enc_dz2[tb]; p.W = ew[tb].w2; p.Zx = g->enc_z1[tb]; p.dX = g->enc_dz1[tb]; p.M_ = n; p.N_ = CCSP_HH; p.K_ = CCSP_H;
     if ((rc = launch_gemm(p, n, CCSP_HH, 1, st))) return rc;

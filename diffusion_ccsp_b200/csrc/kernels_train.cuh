@@ -195,27 +195,40 @@ __global__ void k_reduce_parts(const float *part, int slices, size_t count, floa
   out[i] = s;
 }
 
-// column sums over a row range, fixed order:  out[j] = sum_{r in [r0, r1)} M[r * ld + j]      (bias gradients)
-// grid.x = ceil(cols / 32), grid.y = group; block = 32 columns x 8 row lanes
+// column sums over a row range, fixed order:  out[g][j] = sum_{r in [start[g], start[g+1])} M[r * ld + j]      (bias gradients)
+// two stages so that long ranges are not one block's serial loop: grid (ceil(cols / 32), groups, slices) writes
+// part[slice][g][j] (each block: 32 columns x 8 row lanes over its slice of the range), k_colsum_finish adds the slices in order
+constexpr int COLSUM_SLICES = 32;
 struct ColSumArgs {
   const float *M;
-  int ld, cols;
+  int ld, cols, groups;
   int start[MAX_TYPES + 1];      // row range per group (grid.y)
+  float *part;                   // [COLSUM_SLICES, groups, cols]
   float *out;                    // [groups, cols]
 };
 __global__ void __launch_bounds__(256) k_colsum(const ColSumArgs A) {
   __shared__ float red[8][33];
-  const int g = blockIdx.y, col = blockIdx.x * 32 + (threadIdx.x & 31), lane_r = threadIdx.x >> 5;
+  const int g = blockIdx.y, z = blockIdx.z, col = blockIdx.x * 32 + (threadIdx.x & 31), lane_r = threadIdx.x >> 5;
+  const int r0 = A.start[g], r1 = A.start[g + 1];
+  const int chunk = (r1 - r0 + COLSUM_SLICES - 1) / COLSUM_SLICES;
+  const int b = r0 + z * chunk, e = min(r1, b + chunk);
   float s = 0.f;
   if (col < A.cols)
-    for (int r = A.start[g] + lane_r; r < A.start[g + 1]; r += 8) s += A.M[(size_t)r * A.ld + col];
+    for (int r = b + lane_r; r < e; r += 8) s += A.M[(size_t)r * A.ld + col];
   red[lane_r][threadIdx.x & 31] = s;
   __syncthreads();
   if (lane_r == 0 && col < A.cols) {
     float t = 0.f;
     for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x & 31];
-    A.out[(size_t)g * A.cols + col] = t;
+    A.part[((size_t)z * A.groups + g) * A.cols + col] = t;
   }
+}
+__global__ void k_colsum_finish(const ColSumArgs A) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;       // (g, col)
+  if (i >= A.groups * A.cols) return;
+  float t = 0.f;
+  for (int z = 0; z < COLSUM_SLICES; ++z) t += A.part[(size_t)z * A.groups * A.cols + i];
+  A.out[i] = t;
 }
 
 // ---- encoders, first layer (K = G <= 8): z1 = X[:, off:off+G] W0^T + b0, a1 = silu(z1) ---------------------------
@@ -252,30 +265,33 @@ __global__ void __launch_bounds__(256) k_enc1_bwd(const float *X, int ldx, int o
 }
 
 // ---- time MLP (denoise_fn.py:43-50, 259-264), one t per batch -------------------------------------------------------
-// grid 1, block 256:  emb -> z1 [1024] -> a1 = mish(z1) -> temb [256]
-__global__ void __launch_bounds__(256) k_time_fwd(int t, const float *W1, const float *b1, const float *W3, const float *b3,
-                                                  float *emb, float *z1, float *a1, float *temb) {
-  __shared__ float se[CCSP_H], sa[4 * CCSP_H];
-  const int tid = threadIdx.x;
-  {
-    const float e = (float)(-(log(10000.0) / (CCSP_HH - 1)));
-    const int k = tid & (CCSP_HH - 1);
-    const float arg = (float)t * expf((float)k * e);
-    const float v = tid < CCSP_HH ? sinf(arg) : cosf(arg);
-    se[tid] = v; emb[tid] = v;
+// y[j] = act(b[j] + sum_k W[j, k] x[k]): one warp per output row (coalesced reads of the row, fixed-order tree), 8 rows per block.
+// MODE 0: x = sinusoidal embedding of t (computed here, also stored to `emb`), act = mish, stores z and mish(z)
+// MODE 1: x given, no activation
+template <int MODE>
+__global__ void __launch_bounds__(256) k_time_gemv(int t, const float *freqs, const float *xin, const float *W, const float *b, int N, int K,
+                                                   float *emb, float *z, float *y) {
+  extern __shared__ float sx[];
+  if (MODE == 0) {
+    for (int i = threadIdx.x; i < CCSP_H; i += 256) {
+      const float arg = (float)t * freqs[i & (CCSP_HH - 1)];
+      const float v = i < CCSP_HH ? sinf(arg) : cosf(arg);
+      sx[i] = v;
+      if (blockIdx.x == 0) emb[i] = v;
+    }
+  } else {
+    for (int i = threadIdx.x; i < K; i += 256) sx[i] = xin[i];
   }
   __syncthreads();
-  for (int j = tid; j < 4 * CCSP_H; j += 256) {
-    float s = b1[j];
-    for (int k = 0; k < CCSP_H; ++k) s = fmaf(W1[(size_t)j * CCSP_H + k], se[k], s);
-    z1[j] = s;
-    const float m = mish_f(s);
-    a1[j] = m; sa[j] = m;
+  const int j = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (j >= N) return;
+  float s = 0.f;
+  for (int k = lane; k < K; k += 32) s = fmaf(W[(size_t)j * K + k], sx[k], s);
+  for (int off = 16; off; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  if (lane == 0) {
+    s += b[j];
+    if (MODE == 0) { z[j] = s; y[j] = mish_f(s); } else { y[j] = s; }
   }
-  __syncthreads();
-  float s = b3[tid];
-  for (int k = 0; k < 4 * CCSP_H; ++k) s = fmaf(W3[(size_t)tid * 4 * CCSP_H + k], sa[k], s);
-  temb[tid] = s;
 }
 // bias_c[o] = b_c[o] + sum_k W_c[o, tcol + k] temb[k]            grid (C), block 512
 __global__ void __launch_bounds__(512) k_time_bias_fwd(PtrTable W, PtrTable b, int Kin, int tcol, const float *temb, float *bias) {
@@ -289,46 +305,52 @@ __global__ void __launch_bounds__(512) k_time_bias_fwd(PtrTable W, PtrTable b, i
   bias[c * CCSP_H2 + o] = s;
 }
 // time columns of dW_c and the gradient of temb:  dW_c[o, tcol + k] = db_c[o] temb[k];  dtemb[k] = sum_c sum_o W_c[o, tcol + k] db_c[o]
-// grid (C + 1): blocks 0..C-1 write the outer products, block C reduces dtemb (types in order => deterministic)
-__global__ void __launch_bounds__(256) k_time_cols_bwd(PtrTable W, MutPtrTable dW, int C, int Kin, int tcol, const float *temb,
-                                                        const float *dbias /*[C,512]*/, const int *type_rows, float *dtemb) {
-  const int k = threadIdx.x;
-  if ((int)blockIdx.x < C) {
-    const int c = blockIdx.x;
-    if (dW.p[c] == nullptr) return;
-    const float tk = temb[k];
-    for (int o = 0; o < CCSP_H2; ++o) dW.p[c][(size_t)o * Kin + tcol + k] = dbias[c * CCSP_H2 + o] * tk;
-  } else {
-    float s = 0.f;
-    for (int c = 0; c < C; ++c) {
-      if (type_rows[c] == 0) continue;                     // types without edges are not part of the graph (denoise_fn.py:514-515)
-      for (int o = 0; o < CCSP_H2; ++o) s = fmaf(W.p[c][(size_t)o * Kin + tcol + k], dbias[c * CCSP_H2 + o], s);
-    }
-    dtemb[k] = s;
+// grid (C, 8): block (c, s) handles output rows o in [64 s, 64 s + 64): writes its outer-product rows and the partial
+// dtemb_part[c][s][k]; k_time_bwd adds the partials in (c, s) order => deterministic
+__global__ void __launch_bounds__(256) k_time_cols_bwd(PtrTable W, MutPtrTable dW, int Kin, int tcol, const float *temb,
+                                                        const float *dbias /*[C,512]*/, const int *type_rows, float *dtemb_part) {
+  const int c = blockIdx.x, sl = blockIdx.y, k = threadIdx.x;
+  const float tk = temb[k];
+  float s = 0.f;
+  const bool live = type_rows[c] != 0;                     // types without edges are not part of the graph (denoise_fn.py:514-515)
+  for (int o = sl * 64; o < sl * 64 + 64; ++o) {
+    const float d = dbias[c * CCSP_H2 + o];
+    dW.p[c][(size_t)o * Kin + tcol + k] = d * tk;
+    if (live) s = fmaf(W.p[c][(size_t)o * Kin + tcol + k], d, s);
   }
+  dtemb_part[((size_t)c * 8 + sl) * CCSP_H + k] = s;
 }
-// back through the time MLP: grid 1, block 256
-__global__ void __launch_bounds__(256) k_time_bwd(const float *dtemb, const float *emb, const float *z1, const float *a1, const float *W3,
-                                                  float *dW1, float *db1, float *dW3, float *db3) {
-  __shared__ float sd[CCSP_H], sdz[4 * CCSP_H], se[CCSP_H];
-  const int tid = threadIdx.x;
-  sd[tid] = dtemb[tid]; se[tid] = emb[tid];
-  db3[tid] = dtemb[tid];
-  __syncthreads();
-  for (int j = tid; j < 4 * CCSP_H; j += 256) {
+// back through the time MLP.  grid (64), block 256: every block recomputes dtemb (C*8 partials) and dz1 = (W3^T dtemb) * mish'(z1)
+// for its 16 hidden units, then writes its slices of the two outer products
+__global__ void __launch_bounds__(256) k_time_bwd(const float *dtemb_part, int nparts, const float *emb, const float *z1, const float *a1,
+                                                  const float *W3, float *dW1, float *db1, float *dW3, float *db3) {
+  __shared__ float sd[CCSP_H], se[CCSP_H], sdz[16], sa[16];
+  const int tid = threadIdx.x, j0 = blockIdx.x * 16;
+  {
     float s = 0.f;
-    for (int k = 0; k < CCSP_H; ++k) s = fmaf(W3[(size_t)k * 4 * CCSP_H + j], sd[k], s);
-    const float dz = s * dmish_f(z1[j]);
-    sdz[j] = dz; db1[j] = dz;
+    for (int p = 0; p < nparts; ++p) s += dtemb_part[(size_t)p * CCSP_H + tid];
+    sd[tid] = s; se[tid] = emb[tid];
+    if (blockIdx.x == 0) db3[tid] = s;
   }
   __syncthreads();
-  for (int i = tid; i < CCSP_H * 4 * CCSP_H; i += 256) {
-    const int k = i / (4 * CCSP_H), j = i % (4 * CCSP_H);
-    dW3[i] = sd[k] * a1[j];                                 // dW3[k, j]
+  {  // 16 hidden units of this block: 16 lanes per unit over k, fixed-order tree
+    const int u = tid >> 4, l = tid & 15, j = j0 + u;
+    float s = 0.f;
+    for (int k = l; k < CCSP_H; k += 16) s = fmaf(W3[(size_t)k * 4 * CCSP_H + j], sd[k], s);
+    for (int off = 8; off; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off, 16);
+    if (l == 0) {
+      const float dz = s * dmish_f(z1[j]);
+      sdz[u] = dz; db1[j] = dz; sa[u] = a1[j];
+    }
   }
-  for (int i = tid; i < 4 * CCSP_H * CCSP_H; i += 256) {
-    const int j = i / CCSP_H, k = i % CCSP_H;
-    dW1[i] = sdz[j] * se[k];                                // dW1[j, k]
+  __syncthreads();
+  for (int i = tid; i < CCSP_H * 16; i += 256) {            // dW3[k, j0 + u] = dtemb[k] a1[j]
+    const int k = i >> 4, u = i & 15;
+    dW3[(size_t)k * 4 * CCSP_H + j0 + u] = sd[k] * sa[u];
+  }
+  for (int i = tid; i < 16 * CCSP_H; i += 256) {            // dW1[j0 + u, k] = dz1[j] emb[k]
+    const int u = i >> 8, k = i & 255;
+    dW1[(size_t)(j0 + u) * CCSP_H + k] = sdz[u] * se[k];
   }
 }
 

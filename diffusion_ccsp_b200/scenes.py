@@ -132,18 +132,20 @@ class SceneLoader:
     scenes: yields collated SceneBatch objects of `batch_size` scenes (the last one may be smaller), reshuffled every epoch."""
 
     def __init__(self, pool, batch_size: int, shuffle: bool = False, seed: int = 0):
-        self.scenes = ([pool.select_scenes(i, i + 1) for i in range(pool.num_graphs)] if isinstance(pool, SceneBatch)
-                       else list(pool))
+        if not isinstance(pool, SceneBatch):
+            pool = collate(list(pool))
+        self.pool = pool
         self.batch_size, self.shuffle = int(batch_size), shuffle
         self._rng = np.random.default_rng(seed)
 
     def __len__(self):
-        return (len(self.scenes) + self.batch_size - 1) // self.batch_size
+        return (self.pool.num_graphs + self.batch_size - 1) // self.batch_size
 
     def __iter__(self):
-        order = self._rng.permutation(len(self.scenes)) if self.shuffle else np.arange(len(self.scenes))
-        for i in range(0, len(order), self.batch_size):
-            yield collate([self.scenes[j] for j in order[i:i + self.batch_size]])
+        G = self.pool.num_graphs
+        order = self._rng.permutation(G) if self.shuffle else np.arange(G)
+        for i in range(0, G, self.batch_size):
+            yield _gather_scenes_fast(self.pool, order[i:i + self.batch_size])
 
 
 # =====================================================================================
@@ -253,10 +255,10 @@ def make_batch(kind: str, num_scenes: int, n_obj: int, seed: int = 0) -> SceneBa
 
 
 # -------------------------------------------------------------------------------------
-# RandomSplitQualitativeWorld scenes: committed fixtures generated with the reference's own
-# scene generator + qualitative labeller (tests/golden/make_scenes.py); tiled to any batch.
+# RandomSplitQualitativeWorld scenes: committed fixtures (diffusion_ccsp_b200/data/) generated with the reference's own
+# scene generator + qualitative labeller (tests/golden/make_scenes.py, scripts/make_train_pool.py); tiled to any batch.
 # -------------------------------------------------------------------------------------
-_FIXTURE_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests', 'golden')
+_FIXTURE_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'data')
 
 
 def load_scene_fixture(path: str) -> SceneBatch:
@@ -267,7 +269,7 @@ def load_scene_fixture(path: str) -> SceneBatch:
 def qualitative_batch(num_scenes: int, n_obj: int = 8, seed: int = 0,
                       fixture_dir: Optional[str] = None) -> SceneBatch:
     """`num_scenes` RandomSplitQualitativeWorld scenes with `n_obj` tiles.  Scenes are drawn from
-    the committed fixture pool `tests/golden/scenes_qualitative_n{n_obj}.npz`; when more scenes than
+    the committed fixture pool `diffusion_ccsp_b200/data/scenes_qualitative_n{n_obj}.npz`; when more scenes than
     the pool holds are requested the pool is re-sampled with a seeded permutation (scenes are
     independent, so repeats only matter for statistics, not for the work per scene)."""
     path = os.path.join(fixture_dir or _FIXTURE_DIR, f'scenes_qualitative_n{n_obj}.npz')
@@ -280,20 +282,36 @@ def qualitative_batch(num_scenes: int, n_obj: int = 8, seed: int = 0,
     return _gather_scenes_fast(pool, ids)
 
 
+def qualitative_train_pool(path: Optional[str] = None) -> SceneBatch:
+    """The committed TRAINING pool (24 000 RandomSplitQualitativeWorld scenes with 2..8 tiles, scripts/make_train_pool.py):
+    disjoint draws from the evaluation fixtures, stored with scene-local edge ids."""
+    z = np.load(path or os.path.join(_FIXTURE_DIR, 'scenes_qualitative_train.npz'))
+    ncount, ecount = z['nodes_per_scene'].astype(np.int64), z['edges_per_scene'].astype(np.int64)
+    off = np.concatenate([[0], np.cumsum(ncount)])[:-1]
+    ei = z['edge_local'].astype(np.int64) + np.repeat(off, ecount)[None, :]
+    mask = np.zeros(int(ncount.sum()), np.int8)
+    mask[off] = 1
+    return SceneBatch(z['x'], ei, z['edge_attr'].astype(np.float32), mask)
+
+
 def _gather_scenes_fast(pool: SceneBatch, ids: np.ndarray) -> SceneBatch:
-    """Vectorised take_scenes for large batches."""
-    off = pool.scene_node_ranges()
-    esid = pool.edge_extract.to(torch.int64).numpy()
-    order = np.argsort(esid, kind='stable')
-    ecount = np.bincount(esid, minlength=pool.num_graphs)
-    eoff = np.concatenate([[0], np.cumsum(ecount)])
-    xs, eis, eas, ms = [], [], [], []
-    x, ei, ea, m = pool.x.numpy(), pool.edge_index.numpy(), pool.edge_attr.numpy(), pool.mask.numpy()
-    noff = 0
-    for s in ids:
-        n0, n1 = off[s], off[s + 1]
-        sel = order[eoff[s]:eoff[s + 1]]
-        xs.append(x[n0:n1]); ms.append(m[n0:n1])
-        eis.append(ei[:, sel] - n0 + noff); eas.append(ea[sel])
-        noff += n1 - n0
-    return SceneBatch(np.concatenate(xs), np.concatenate(eis, 1), np.concatenate(eas), np.concatenate(ms))
+    """Vectorised take_scenes for large batches (per-pool offset tables are computed once and kept on the pool)."""
+    tab = getattr(pool, '_gather_tables', None)
+    if tab is None:
+        off = pool.scene_node_ranges()
+        esid = pool.edge_extract.to(torch.int64).numpy()
+        order = np.argsort(esid, kind='stable')
+        eoff = np.concatenate([[0], np.cumsum(np.bincount(esid, minlength=pool.num_graphs))])
+        ei = pool.edge_index.numpy()[:, order]
+        ei_local = ei - off[esid[order]][None, :]                    # node ids relative to the scene's first node
+        tab = pool._gather_tables = (off, eoff, pool.x.numpy(), ei_local, pool.edge_attr.numpy()[order], pool.mask.numpy())
+    off, eoff, x, ei_local, ea, m = tab
+    ids = np.asarray(ids, dtype=np.int64)
+    ncount, ecount = off[ids + 1] - off[ids], eoff[ids + 1] - eoff[ids]
+    new_off = np.concatenate([[0], np.cumsum(ncount)])
+    nsel = np.concatenate([np.arange(off[s], off[s + 1]) for s in ids]) if ids.size else np.zeros(0, np.int64)
+    esel = np.concatenate([np.arange(eoff[s], eoff[s + 1]) for s in ids]) if ids.size else np.zeros(0, np.int64)
+    shift = np.repeat(new_off[:-1], ecount)
+    sid_n = np.repeat(np.arange(ids.size), ncount).astype(np.float32)
+    sid_e = np.repeat(np.arange(ids.size), ecount).astype(np.float32)
+    return SceneBatch(x[nsel], ei_local[:, esel] + shift[None, :], ea[esel], m[nsel], sid_n, sid_e, pool.world_dims)

@@ -93,8 +93,7 @@ def make_trained_state_dict(fixture_path: str = None) -> Dict[str, torch.Tensor]
     the reference's own loss) overlaid.  With it the sampler stays at |x| = O(1) like a real checkpoint."""
     import os
     if fixture_path is None:
-        fixture_path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests', 'golden',
-                                    'trained_small_qualitative.npz')
+        fixture_path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'data', 'trained_small_qualitative.npz')
     z = np.load(fixture_path)
     sd = make_state_dict(DIMS['qualitative'], 'qualitative', seed=int(z['weight_seed']))
     for k in z.files:

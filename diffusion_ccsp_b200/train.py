@@ -167,7 +167,9 @@ class _DiffusionLoss(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_out):
-        return (None,) * 8 + tuple(None if g is None else g * grad_out for g in ctx.grads)
+        live = [g for g in ctx.grads if g is not None]
+        torch._foreach_mul_(live, grad_out)           # one multi-tensor launch; the buffers belong to this call
+        return (None,) * 8 + tuple(ctx.grads)
 
 
 def diffusion_loss(denoise_fn, graph: TrainGraph, t: int, sqrt_ac: float, sqrt_1mac: float, noise: torch.Tensor,

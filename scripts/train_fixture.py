@@ -32,18 +32,22 @@ def main():
     ap.add_argument('--eval-scenes', type=int, default=256)
     ap.add_argument('--out', default='gpurun_out/ckpt')
     ap.add_argument('--seed', type=int, default=0)
+    ap.add_argument('--init', default=None, help='state dict (.pt) to start from')
+    ap.add_argument('--lr', type=float, default=5e-4)
     a = ap.parse_args()
     torch.manual_seed(a.seed)
-    pool8 = scenes.qualitative_batch(1024, 8)
-    train_pool = scenes.collate([pool8.select_scenes(512, 1024), scenes.qualitative_batch(64, 4), scenes.qualitative_batch(16, 6),
-                                 scenes.qualitative_batch(16, 3)])
-    eval_batch = pool8.select_scenes(0, a.eval_scenes)
+    train_pool = scenes.qualitative_train_pool()                      # 24 000 scenes, 2..8 tiles (scripts/make_train_pool.py)
+    eval_batch = scenes.qualitative_batch(a.eval_scenes, 8)           # evaluation fixtures: disjoint draws
+    eval4 = scenes.qualitative_batch(64, 4)
     dims = synthetic.DIMS['qualitative']
     sd = synthetic.make_state_dict(dims, 'qualitative', seed=0)
     tr = create_trainer('qualitative', timesteps=a.timesteps, EBM='ULA', train_dataset=train_pool, train_num_steps=0,
-                        train_batch_size=a.batch, results_folder=a.out, render_dir=a.out, device='cuda')
+                        train_batch_size=a.batch, train_lr=a.lr, results_folder=a.out, render_dir=a.out, device='cuda')
+    if a.init:
+        sd = {k: v.float() for k, v in torch.load(a.init, map_location='cpu').items()}
     tr.model.load_state_dict(sd, strict=False)
     checker = SolvedChecker(eval_batch, dims, 'qualitative', 'cuda')
+    checker4 = SolvedChecker(eval4, dims, 'qualitative', 'cuda')
     log = dict(steps=[], loss=[], solved=[], train_s=[], config=vars(a))
     t_train = 0.0
     done = 0
@@ -58,20 +62,22 @@ def main():
         poses = tr.model.sample(eval_batch, seed=1)
         solved, counts = checker(poses, return_counts=True)
         frac = float(solved.float().mean())
+        frac4 = float(checker4(tr.model.sample(eval4, seed=2)).float().mean())
         free = poses[~eval_batch.mask.bool().cuda()]
-        print(f'[fixture] step {done}: loss {tr.loss_log[-1][1]:.5f}  solved {frac:.3f}  collisions {(counts[:, 0] > 0).float().mean():.3f} '
+        print(f'[fixture] step {done}: loss {tr.loss_log[-1][1]:.5f}  solved N=8 {frac:.3f} N=4 {frac4:.3f}  collisions {(counts[:, 0] > 0).float().mean():.3f} '
               f'missing {(counts[:, 1] > 0).float().mean():.3f}  max|x| {float(free.abs().max()):.2f}  train {t_train:.1f}s', flush=True)
-        log['steps'].append(done); log['loss'].append(tr.loss_log[-1][1]); log['solved'].append(frac); log['train_s'].append(t_train)
+        log['steps'].append(done); log['loss'].append(tr.loss_log[-1][1]); log['solved'].append(frac); log.setdefault('solved_n4', []).append(frac4); log['train_s'].append(t_train)
     os.makedirs(a.out, exist_ok=True)
     tr.step = done
     tr.save('fixture')
     half = {k: v.half() for k, v in tr.model.state_dict().items() if k.startswith('denoise_fn.')}
     torch.save(half, os.path.join(a.out, 'denoise_fn_fp16.pt'))
+    np.savez_compressed(os.path.join(a.out, 'denoise_fn_fp16.npz'), **{k: v.cpu().numpy() for k, v in half.items()})
     log['loss_log'] = tr.loss_log
     log['ms_per_step'] = t_train / max(done, 1) * 1e3
     with open(os.path.join(a.out, 'train_log.json'), 'w') as f:
         json.dump(log, f)
-    print(json.dumps(dict(steps=done, final_loss=log['loss'][-1], solved=log['solved'], ms_per_train_step=log['ms_per_step'])))
+    print(json.dumps(dict(steps=done, final_loss=log['loss'][-1], solved=log['solved'], solved_n4=log['solved_n4'], ms_per_train_step=log['ms_per_step'])))
 
 
 if __name__ == '__main__':

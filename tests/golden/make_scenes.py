@@ -10,7 +10,7 @@ and restates the few trimesh-dependent lines that cannot be imported here:
   envs/worlds.py:279-286 + networks/data_transforms.py:101-109  node rows
       [w/W, l/L, x/(W/2), y/(L/2), cs, sn], yaw = pi/2 (or pi with w,l swapped when l > w)
 
-Output: tests/golden/scenes_qualitative_n{N}.npz  (x f32 [n,6], edge_index i32 [2,E],
+Output: diffusion_ccsp_b200/data/scenes_qualitative_n{N}.npz  (x f32 [n,6], edge_index i32 [2,E],
 edge_attr i8 [E], mask i8 [n]).     python tests/golden/make_scenes.py
 """
 import math
@@ -84,7 +84,7 @@ def main():
             x, ei, ea, m = one_scene(builders, data_utils, qual, n_obj)
             xs.append(x); eis.append(ei + off); eas.append(ea); ms.append(m)
             off += x.shape[0]
-        out = os.path.join(HERE, f'scenes_qualitative_n{n_obj}.npz')
+        out = os.path.join(os.path.dirname(os.path.dirname(HERE)), 'diffusion_ccsp_b200', 'data', f'scenes_qualitative_n{n_obj}.npz')
         np.savez_compressed(out, x=np.concatenate(xs), edge_index=np.concatenate(eis, 1),
                             edge_attr=np.concatenate(eas), mask=np.concatenate(ms))
         E = sum(e.shape[0] for e in eas)

@@ -7,7 +7,7 @@ only pose_encoder, pose_decoder and the mlps' biases (~70 k parameters) are trai
 at synthetic.make_state_dict(seed) values and is regenerated from the seed.
 
 Build-container only.   python tests/golden/make_trained_fixture.py
-Output: tests/golden/trained_small_qualitative.npz  +  goldens trained_traj_qualitative_T{100,1000}.npz
+Output: diffusion_ccsp_b200/data/trained_small_qualitative.npz  +  goldens trained_traj_qualitative_T{100,1000}.npz
 """
 import os
 import sys
@@ -58,7 +58,7 @@ def main():
             print(f'step {step} loss {loss.item():.4f} ({time.time() - t0:.0f}s)', flush=True)
     gd.eval()
     sd = {k: v.detach().numpy().copy() for k, v in gd.state_dict().items() if trainable(k)}
-    np.savez_compressed(os.path.join(HERE, 'trained_small_qualitative.npz'), weight_seed=SEED, **sd)
+    np.savez_compressed(os.path.join(os.path.dirname(os.path.dirname(HERE)), 'diffusion_ccsp_b200', 'data', 'trained_small_qualitative.npz'), weight_seed=SEED, **sd)
     print('saved', sum(v.size for v in sd.values()), 'floats')
 
     # goldens in the realistic regime: config 1 shape, T = 100 (and T = 1000 on 2 scenes)
