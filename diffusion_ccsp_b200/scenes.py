@@ -67,7 +67,12 @@ class SceneBatch:
 
     @property
     def num_graphs(self) -> int:
-        return int(self.x_extract.max().item()) + 1 if self.num_nodes else 0
+        """scenes in the batch; ids are 0..S-1 after `collate` (a single dataset item may carry its dataset index instead,
+        data_transforms.py:197-198)"""
+        if not self.num_nodes:
+            return 0
+        lo, hi = int(self.x_extract.min().item()), int(self.x_extract.max().item())
+        return hi - lo + 1
 
     def clone(self) -> "SceneBatch":
         return SceneBatch(self.x.clone(), self.edge_index.clone(), self.edge_attr.clone(),
@@ -91,10 +96,10 @@ class SceneBatch:
         n0, n1 = int(off[lo]), int(off[hi])
         esid = self.edge_extract.to(torch.int64)
         keep = (esid >= lo) & (esid < hi)
+        wd = self.world_dims[lo:hi] if isinstance(self.world_dims, list) and len(self.world_dims) == self.num_graphs else self.world_dims
         return SceneBatch(self.x[n0:n1].clone(), self.edge_index[:, keep] - n0,
                           self.edge_attr[keep].clone(), self.mask[n0:n1].clone(),
-                          self.x_extract[n0:n1] - lo, self.edge_extract[keep] - lo,
-                          self.world_dims)
+                          self.x_extract[n0:n1] - lo, self.edge_extract[keep] - lo, wd)
 
     def shard(self, rank: int, world_size: int) -> "SceneBatch":
         """Contiguous, near-equal scene shard for `rank` (no scene is split)."""
@@ -113,14 +118,20 @@ def collate(scenes: Sequence[SceneBatch]) -> SceneBatch:
     xs, eis, eas, ms, xe, ee = [], [], [], [], [], []
     off = 0
     sid = 0
+    wd = []
     for s in scenes:
         g = s.num_graphs
+        base = s.x_extract.min() if s.num_nodes else 0          # dataset items carry their dataset index: re-base to 0..S-1
         xs.append(s.x); eis.append(s.edge_index + off); eas.append(s.edge_attr); ms.append(s.mask)
-        xe.append(s.x_extract + sid); ee.append(s.edge_extract + sid)
+        xe.append(s.x_extract - base + sid); ee.append(s.edge_extract - base + sid)
         off += s.num_nodes
         sid += g
+        wd.append(s.world_dims)
+    world_dims = None
+    if all(w is not None for w in wd):                           # PyG collation concatenates the per-item world_dims lists
+        world_dims = [tuple(d) for w in wd for d in w]
     return SceneBatch(torch.cat(xs), torch.cat(eis, 1), torch.cat(eas), torch.cat(ms),
-                      torch.cat(xe), torch.cat(ee))
+                      torch.cat(xe), torch.cat(ee), world_dims)
 
 
 def take_scenes(batch: SceneBatch, ids: Sequence[int]) -> SceneBatch:
@@ -314,4 +325,7 @@ def _gather_scenes_fast(pool: SceneBatch, ids: np.ndarray) -> SceneBatch:
     shift = np.repeat(new_off[:-1], ecount)
     sid_n = np.repeat(np.arange(ids.size), ncount).astype(np.float32)
     sid_e = np.repeat(np.arange(ids.size), ecount).astype(np.float32)
-    return SceneBatch(x[nsel], ei_local[:, esel] + shift[None, :], ea[esel], m[nsel], sid_n, sid_e, pool.world_dims)
+    wd = pool.world_dims
+    if isinstance(wd, list) and len(wd) == pool.num_graphs:
+        wd = [wd[int(s)] for s in ids]
+    return SceneBatch(x[nsel], ei_local[:, esel] + shift[None, :], ea[esel], m[nsel], sid_n, sid_e, wd)

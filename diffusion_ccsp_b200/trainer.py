@@ -183,23 +183,49 @@ def create_trainer(input_mode='qualitative', timesteps=1000, EBM='ULA', samples_
                    results_folder=results_folder, EBM=EBM, input_mode=input_mode, **kwargs)
 
 
-def load_trainer(run_id, milestone, logs_dir='./logs', **kwargs) -> Trainer:
-    """train_utils.py:340-354: build the trainer for `run_id` and load `logs/<run_id>/model-<milestone>.pt`.
-    The reference recovers the run's flags from wandb/<run>/files/config.yaml; here they are passed as kwargs
-    (or read from logs/<run_id>/config.json when present)."""
-    cfg_path = os.path.join(logs_dir, str(run_id), 'config.json')
-    cfg = json.load(open(cfg_path)) if os.path.exists(cfg_path) else {}
-    cfg.update(kwargs)
-    trainer = create_trainer(results_folder=os.path.join(logs_dir, str(run_id)), **cfg)
+def load_trainer(run_id, milestone, logs_dir='./logs', wandb_roots=('wandb', 'wandb2'), test_datasets=None, data_root='data',
+                 **kwargs) -> Trainer:
+    """train_utils.py:340-354: recover the run's flags from wandb/<run>/files/config.yaml (`data_io.get_args_from_run_id`),
+    build the trainer and load logs/<run_id>/model-<milestone>.pt (ddpm.py:503-514).  Keyword arguments override the
+    recovered flags (the reference allows input_mode / train_task / test_tasks / train_num_steps, train_utils.py:344-347);
+    when there is no wandb directory for the run the flags come from the keyword arguments alone.  Test datasets named by
+    `test_tasks` are read from `data_root` when present (`data_io.GraphDataset`)."""
+    from . import data_io
+    try:
+        args = vars(data_io.get_args_from_run_id(str(run_id), wandb_roots))
+    except FileNotFoundError:
+        args = dict(data_io.ARG_DEFAULTS, run_id=str(run_id), input_mode=kwargs.get('input_mode', 'qualitative'),
+                    EBM=kwargs.get('EBM', 'ULA'))
+    args.update(kwargs)
+    if args.get('model', 'Diffusion-CCSP') != 'Diffusion-CCSP' or args.get('energy_wrapper'):
+        raise NotImplementedError('StructDiffusion / energy-wrapper runs are outside the accelerated path (SURVEY.md §2 #3, #6)')
+    input_mode = args['input_mode']
+    if test_datasets is None and args.get('test_tasks'):
+        test_datasets = {}
+        for k, task in args['test_tasks'].items():
+            if input_mode not in task:
+                task = task.replace('_test', f'_{input_mode}_test')                 # train_utils.py:243-250
+            if os.path.isdir(os.path.join(data_root, task, 'raw')):
+                ds = data_io.GraphDataset(task, input_mode, root=data_root)
+                from .scenes import SceneLoader
+                test_datasets[k] = list(SceneLoader(ds.scenes, 100, shuffle=False))      # ddpm.py:446-449 (batch size 100)
+    keep = ('timesteps', 'EBM', 'samples_per_step', 'step_sizes', 'hidden_dim', 'normalize', 'train_task', 'train_num_steps')
+    cfg = {k: args[k] for k in keep if k in args and args[k] is not None}
+    for k in ('device', 'math', 'render_dir'):
+        if k in kwargs:
+            cfg[k] = kwargs[k]
+    trainer = create_trainer(input_mode=input_mode, test_datasets=test_datasets,
+                             results_folder=os.path.join(logs_dir, str(run_id)), **cfg)
     trainer.load(milestone)
     return trainer
 
 
 def evaluate_model(run_id, milestone, tries=(10, 0), json_name='eval', save_log=True, run_all=False, render=True,
                    run_only=False, resume_eval=False, render_name_extra=None, return_history=False, **kwargs):
-    """solve_csp.py:19-28."""
+    """solve_csp.py:19-28.  Extra keyword `checker=` (a `(rows, batch) -> list[bool]` callback) replaces the GPU solved-checker."""
+    checker = kwargs.pop('checker', None)
     trainer = load_trainer(run_id, milestone, **kwargs)
     if render_name_extra is not None:
         trainer.render_dir += f'_{render_name_extra}'
     return trainer.evaluate(json_name, tries=tries, render=render, save_log=save_log, run_all=run_all, run_only=run_only,
-                            resume_eval=resume_eval, return_history=return_history)
+                            resume_eval=resume_eval, return_history=return_history, checker=checker)

@@ -45,6 +45,13 @@ def _stub(name, **attrs):
 _loaded = {}
 
 
+class _DataStub:
+    """torch_geometric.data.Data as the reference's transforms use it: a keyword bag (data_transforms.py:195-199)."""
+
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+
 def load_reference():
     """Returns (denoise_fn_module, ddpm_module) of the unmodified reference."""
     if "mods" in _loaded:
@@ -64,7 +71,7 @@ def load_reference():
     _stub("imageio")
     _stub("torch_geometric")
     _stub("torch_geometric.loader", DataLoader=object)
-    _stub("torch_geometric.data", Data=object)
+    _stub("torch_geometric.data", Data=_DataStub)
     for p in ("networks", "envs", ""):
         path = os.path.join(REFERENCE_ROOT, p) if p else REFERENCE_ROOT
         if path not in sys.path:
