@@ -7,8 +7,10 @@
 
 A "step" is one full `GaussianDiffusion.sample` of the workload BASELINE.json quotes the metric on
 (configs[1]): RandomSplitQualitativeWorld, N=8 objects, T=1000 timesteps, ULA with K=10 steps per
-timestep (11 000 denoiser evaluations), batch = 1024 scenes PER GPU (weak scaling: every rank samples
-its own 1024 scenes; no collective inside the loop, one NCCL all-gather of the final poses per step).
+timestep (11 000 denoiser evaluations), batch = 1024 scenes PER GPU (weak scaling: ONE global batch of
+N x 1024 scenes goes through parallel.ShardedSampler — contiguous scene shards, no collective inside the
+loop, one NCCL all-gather of the final poses per step).  At N > 1 the line also carries `strong`: a fixed
+global batch of 1024 scenes over the N GPUs against the same batch on one GPU.
 
 Prints ONE JSON line (rank 0).  See DESIGN.md §Measurement for every key.
 """
@@ -48,6 +50,8 @@ def parse():
     ap.add_argument('--batch', type=int, default=WORKLOAD['batch_per_gpu'], help='dev only')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-strong', action='store_true', help='N > 1: skip the fixed-global-batch (strong scaling) measurement')
+    ap.add_argument('--no-configs', action='store_true', help='N = 1: skip the extra configs 1/3/4/5 keys')
     return ap.parse_args()
 
 
@@ -207,7 +211,7 @@ def run_reference(args):
         return
     from diffusion_ccsp_b200 import scenes, synthetic
     mode, dims = 'qualitative', synthetic.DIMS['qualitative']
-    sd = synthetic.make_trained_state_dict()
+    sd = synthetic.load_trained_checkpoint()
     batch = scenes.qualitative_batch(args.batch, WORKLOAD['n_obj'])
     T, K = args.timesteps, WORKLOAD['K']
     times, kind = [], None
@@ -253,8 +257,10 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from diffusion_ccsp_b200 import _abi, scenes, synthetic
+    from diffusion_ccsp_b200.checker import SolvedChecker
     from diffusion_ccsp_b200.ddpm import GaussianDiffusion
     from diffusion_ccsp_b200.denoise_fn import ConstraintDiffuser
+    from diffusion_ccsp_b200.parallel import ShardedSampler
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -274,63 +280,74 @@ def run_ours(args):
     math = args.math or default_math()
     mode, dims = 'qualitative', synthetic.DIMS['qualitative']
     P = dims[-1][0]
-    sd = synthetic.make_trained_state_dict()          # realistic O(1) regime (tests/golden/make_trained_fixture.py)
+    sd = synthetic.load_trained_checkpoint()          # trained by this repo's own training step (scripts/train_fixture.py)
     T, K, B = args.timesteps, WORKLOAD['K'], args.batch
-    batch = scenes.qualitative_batch(B, WORKLOAD['n_obj'], seed=rank)       # every rank its own scenes
     den = ConstraintDiffuser(dims=dims, input_mode=mode, device=dev, verbose=False, math=math)
     gd = GaussianDiffusion(den, timesteps=T, EBM='ULA', samples_per_step=K).eval()
     gd.load_state_dict(sd, strict=False)
-
-    n, E = batch.num_nodes, batch.num_edges
-    plan = den.plan_for(batch)                      # inputs resident in HBM before the timed region
-    out = torch.empty((n, P), dtype=torch.float32, device=dev)
-    gathered = torch.empty((world * n, P), dtype=torch.float32, device=dev) if world > 1 else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)          # > 126 MB L2
-    tables, sps = gd._tables(), gd._samples_per_step_table()
-
-    def step(i):
-        flush.zero_()                                                      # L2 flush between steps
-        plan.sample(tables, sps, 1, out, None, seed=1000 + i, node_offset=rank * n)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, out)                     # end-of-run metrics gather
+    uuid = str(torch.cuda.get_device_properties(dev).uuid)
+    uuid = uuid if uuid.startswith('GPU-') else 'GPU-' + uuid
+    evals = T * (1 + K)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    for i in range(args.warmup):
-        step(i)
-    barrier()
-    evals = T * (1 + K)
-    plan.set_timing(max(1, evals // 128))
-    uuid = str(torch.cuda.get_device_properties(dev).uuid)
-    clk = ClockSampler(uuid if uuid.startswith('GPU-') else 'GPU-' + uuid)
-    clk.start()
-    _abi.reset_launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for i in range(args.steps):
-        step(args.warmup + i)
-    e1.record()
-    barrier()
-    clocks = clk.stop()
-    launches = _abi.launch_count()
-    ms = e0.elapsed_time(e1) / args.steps
-    tm = plan.get_timing()
-    plan.set_timing(0)
-    if world > 1:
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    free = out[~batch.mask.bool().to(dev)]
-    result_stats = dict(finite_frac=float(torch.isfinite(free).float().mean()), max_abs=float(free.abs().max()),
-                        frac_in_unit_box=float((free.abs() <= 1.05).float().mean()))
+        return float(t.item())
+
+    def timed_run(sampler, steps, warmup, seed0, timing=False):
+        """W warm-up + K timed steps of the PRODUCT's sharded path (parallel.ShardedSampler: shard -> local loop -> one all-gather),
+        inputs resident in HBM (the shard's plan is compiled before the timed region); CUDA events, barrier + synchronize on
+        both sides, max over ranks."""
+        plan = den.plan_for(sampler.local)
+
+        def step(i):
+            flush.zero_()                                                  # L2 flush between steps
+            return sampler.sample(seed=seed0 + i)                          # global poses on every rank (SURVEY §8e)
+
+        for i in range(warmup):
+            step(i)
+        barrier()
+        if timing:
+            plan.set_timing(max(1, evals // 128))
+        clk = ClockSampler(uuid)
+        clk.start()
+        _abi.reset_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for i in range(steps):
+            full = step(warmup + i)
+        e1.record()
+        barrier()
+        clocks = clk.stop()
+        launches = _abi.launch_count()
+        ms = max_over_ranks(e0.elapsed_time(e1) / steps)
+        tm = plan.get_timing() if timing else None
+        plan.set_timing(0)
+        return ms, full, clocks, launches, tm, plan
+
+    # ---- headline: weak scaling, 1024 scenes per GPU — ONE global batch of world x B scenes through the sharded sampler --------
+    global_batch = scenes.qualitative_batch(world * B, WORKLOAD['n_obj'], seed=0)
+    sampler = ShardedSampler(gd, global_batch)
+    batch = sampler.local
+    n, E = batch.num_nodes, batch.num_edges
+    ms, full, clocks, launches, tm, plan = timed_run(sampler, args.steps, args.warmup, 1000, timing=True)
     value = world * B / (ms / 1e3)
+    out = full[sampler.n0:sampler.n1]
+    free = out[~batch.mask.bool().to(dev)]
+    fin = torch.isfinite(free)
+    result_stats = dict(finite_frac=float(fin.float().mean()), max_abs=float(free[fin].abs().max()),
+                        frac_in_unit_box=float((free.abs() <= 1.05).float().mean()))
 
     # ---- N1: solved fraction of the last step's output (SolvedChecker: one launch, poses stay on the device) -------------
-    from diffusion_ccsp_b200.checker import SolvedChecker
     checker = SolvedChecker(batch, dims, mode, dev)
     solved = checker(out)
     torch.cuda.synchronize(dev)
@@ -349,8 +366,37 @@ def run_ours(args):
     solved_info = dict(solved_frac=solved_frac, solved_scenes=int(st[0]), scenes=int(st[1]), with_collisions=int(st[2]),
                        with_missing_constraints=int(st[3]), check_ms_per_batch=check_ms,
                        checker='k_check_solved (CUDA, 1 launch per batch; clamp + rows + SAT + 13 relations + set inclusion)',
-                       note='weights are a fixture with 74k of 9.15M parameters trained: the solved rate says nothing about the method; '
-                            'the checker itself is parity-tested bit-exactly (tests/test_gpu_checker.py)')
+                       weights='checkpoint trained by this repo (15k Adam steps of ccsp_train_step on 24k generated scenes): far from the '
+                               "paper's 300k-step models, and N = 8 is beyond the sizes the reference trains on (2-5 tiles)")
+    if rank == 0:
+        # the same checkpoint in the regime the reference evaluates (N = 4, solve_csp.py test sets of 2-4 tiles): one try
+        b4 = scenes.qualitative_batch(64, 4)
+        s4 = SolvedChecker(b4, dims, mode, dev)(gd.sample(b4, seed=77))
+        solved_info['n4'] = dict(scenes=64, solved_frac=float(s4.float().mean()), timesteps=T)
+    barrier()
+
+    # ---- strong scaling: a FIXED global batch of B scenes over the N GPUs (B / N per GPU), and the same batch on one GPU -----
+    strong = None
+    if world > 1 and not args.no_strong:
+        gb1 = scenes.qualitative_batch(B, WORKLOAD['n_obj'], seed=0)
+        ssteps = max(1, min(args.steps, 3))
+        ms_n, _, _, _, _, _ = timed_run(ShardedSampler(gd, gb1), ssteps, 1, 3000)
+        den.drop_plans()
+        class _Solo:                                                        # every rank runs the WHOLE batch alone: the N = 1 time
+            local = gb1
+
+            @staticmethod
+            def sample(seed):
+                return gd.p_sample_loop(gb1, seed=seed)
+        solo = _Solo()
+        ms_1, _, _, _, _, _ = timed_run(solo, ssteps, 1, 4000)
+        strong = dict(scaling='strong', global_batch=B, scenes_per_gpu=B // world, ms_per_step=ms_n, value=B / (ms_n / 1e3),
+                      unit='scenes/s', ms_per_step_one_gpu=ms_1, speedup=ms_1 / ms_n, efficiency=ms_1 / ms_n / world, steps=ssteps,
+                      ms_per_evaluation=ms_n / evals,
+                      limit='per-launch fixed cost of the node + edge kernel pair (prologue, first ring fill, tail: ~0.03 ms per evaluation) '
+                            'does not shrink with the shard')
+        den.drop_plans()
+        plan = den.plan_for(batch)
 
     # ---- e2e: public API with HOST buffers: plan build (H2D) + sample + D2H, wall clock ------------
     e2e = None
@@ -366,7 +412,7 @@ def run_ours(args):
             den.drop_plans()
             pl = den.plan_for(pinned)                                    # host batch -> HBM-resident plan (H2D inside)
             tb_ = time.perf_counter()
-            res = gd.sample(pinned, seed=5000 + i, node_offset=rank * n)  # synchronises (reference bookkeeping)
+            res = gd.sample(pinned, seed=5000 + i, node_offset=sampler.n0)  # synchronises (reference bookkeeping)
             tc_ = time.perf_counter()
             host_out.copy_(res, non_blocking=False)
             td = time.perf_counter()
@@ -377,23 +423,24 @@ def run_ours(args):
         for k in e2e_parts:
             e2e_parts[k] = 0.0
         barrier()
-        clk2 = ClockSampler(uuid if uuid.startswith('GPU-') else 'GPU-' + uuid)
+        clk2 = ClockSampler(uuid)
         clk2.start()
         t0 = time.perf_counter()
         nsteps = max(1, min(args.steps, 3))
         for i in range(nsteps):
             h2d = e2e_step(1 + i)
         barrier()
-        dt = (time.perf_counter() - t0) / nsteps
+        dt = max_over_ranks((time.perf_counter() - t0) / nsteps)
         clocks2 = clk2.stop()
-        if world > 1:
-            t = torch.tensor([dt], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
         e2e = dict(value=world * B / dt, unit='scenes/s', h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(n * P * 4),
                    ms_per_step=dt * 1e3, steps=nsteps, clocks=clocks2,
                    breakdown_ms={k: v / nsteps for k, v in e2e_parts.items()},
                    api='GaussianDiffusion.sample(batch) with host batch; plan rebuilt every step')
+
+    # ---- the other BASELINE.json configs at their own per-GPU shard sizes, full T (N = 1 only; extra keys, not the headline) ----
+    configs = None
+    if world == 1 and not args.no_configs:
+        configs = other_configs(dev, math, T, K, flush)
 
     if rank == 0:
         pk = peaks()
@@ -407,6 +454,7 @@ def run_ours(args):
                         achieved=achieved, peak=pk['bf16_sustained'], unit='TFLOP/s',
                         frac=(achieved / pk['bf16_sustained']) if achieved else None,
                         traffic=ncu_traffic('k_edge_fused2_tc' if fused else 'k_edge_l1_tc'),
+                        traffic_source='profiles/ncu_traffic.json (committed ncu --set full capture, not measured in this run)',
                         peak_source=pk['source'] + ': bf16_tflops_sustained (kernel timed inside a long step)',
                         algorithmic_flops_per_launch=dom_flops, avg_launch_ms=l1_ms, launches_sampled=tm['samples'],
                         note=('FP32 FMA validation path: tensor-core fraction is expected to be tiny' if math == 'fp32' else
@@ -414,8 +462,10 @@ def run_ours(args):
         line = dict(metric='scenes_per_sec', value=value, unit='scenes/s', n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=ms, higher_is_better=True, scaling='weak', vs_baseline=None, dtype=math, data='synthetic',
                     config=config_dict(args, T, K, B),
-                    workload_detail=dict(nodes_per_gpu=n, edges_per_gpu=E, weights='seeded init, 74k parameters (pose encoder/decoder, mlps biases) trained offline with the reference loss; 9.15 M params',
-                                noise='in-kernel Philox4x32-10', l2='explicit 256 MiB flush between steps; static term + activations (2 x %d MB) exceed L2' % (plan.edge_rows * 512 * 4 >> 20)),
+                    workload_detail=dict(nodes_per_gpu=n, edges_per_gpu=E, global_scenes=world * B,
+                                         path='parallel.ShardedSampler: one global batch, contiguous scene shards, Philox keyed on the global node id, one all_gather_into_tensor per step',
+                                         weights='diffusion_ccsp_b200/data/denoise_fn_qualitative_fp16.npz: 9.15 M parameters trained by this repo (scripts/train_fixture.py)',
+                                         noise='in-kernel Philox4x32-10', l2='explicit 256 MiB flush between steps; static term + activations (2 x %d MB) exceed L2' % (plan.edge_rows * 512 * 4 >> 20)),
                     clocks=clocks, e2e=e2e, gpu_launches=int(launches), result=result_stats,
                     solved=solved_info, solved_scenes_per_sec=value * solved_frac,
                     roofline=roofline,
@@ -424,9 +474,13 @@ def run_ours(args):
                                  shares_additive=False,
                                  shares_note='the sampling events serialise the PDL-overlapped node/edge pair, so the shares sum to more than 1'),
                     algorithmic_tflops=fl['total'] * evals * world / (ms * 1e-3) / 1e12)
+        if strong is not None:
+            line['strong'] = strong
+        if configs is not None:
+            line['configs'] = configs
         if world == 1 and not args.no_cpu_baseline:
-            full, measured, kind = reference_sample_time(batch, sd, dims, mode, T, K, 1)
-            line['cpu_baseline'] = dict(value=B / full, unit='scenes/s', cores=host_threads(), kind=kind, cpu=cpu_model(),
+            full_s, measured, kind = reference_sample_time(batch, sd, dims, mode, T, K, 1)
+            line['cpu_baseline'] = dict(value=B / full_s, unit='scenes/s', cores=host_threads(), kind=kind, cpu=cpu_model(),
                                         sample=f'1 of {T} timesteps (11 denoiser evaluations, {measured:.1f} s) at the full batch, extrapolated x{T}')
             if kind == 'reference':
                 # the tougher baseline of BASELINE.md §3: the same unmodified PyTorch code with device='cuda' on this B200
@@ -440,6 +494,49 @@ def run_ours(args):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def other_configs(dev, math, T, K, flush):
+    """BASELINE.json configs 1, 3, 4, 5 at full T through the public API (one warm-up sample at T = 20, then one timed sample):
+    device-timed scenes/s of ONE GPU's shard.  Weights are seeded-init (no checkpoint exists for these worlds): throughput only."""
+    import torch
+    from diffusion_ccsp_b200 import scenes, synthetic
+    from diffusion_ccsp_b200.ddpm import GaussianDiffusion
+    from diffusion_ccsp_b200.denoise_fn import ConstraintDiffuser
+    out = {}
+    cases = [
+        ('1', 'qualitative', False, lambda: scenes.qualitative_batch(8, 4), 100, 'RandomSplitQualitativeWorld N=4, T=100, batch=8'),
+        ('3', 'diffuse_pairwise', False, lambda: scenes.make_batch('boxes', 4096, 12, seed=1), T, 'RandomSplitWorld N=12, batch=4096, 1 GPU'),
+        ('4', 'diffuse_pairwise', True, lambda: scenes.make_batch('triangles', 1024, 10, seed=2), T, 'TriangularRandomSplitWorld N=10, batch 8192 / 8 GPUs = 1024 per GPU'),
+        ('5', 'robot_box', False, lambda: scenes.make_batch('robot_box', 256, 6, seed=3), T, '3D panda-box packing N=6, batch 2048 / 8 GPUs = 256 per GPU'),
+    ]
+    for key, mode, tri, factory, Tc, desc in cases:
+        dims = synthetic.dims_for(mode, tri)
+        b = factory()
+        den = ConstraintDiffuser(dims=dims, input_mode=mode, device=dev, verbose=False, math=math)
+        sd = synthetic.make_state_dict(dims, mode, seed=0)
+        warm = GaussianDiffusion(den, timesteps=20, EBM='ULA', samples_per_step=K).eval()
+        warm.load_state_dict(sd, strict=False)
+        warm.sample(b, seed=1)
+        gd = GaussianDiffusion(den, timesteps=Tc, EBM='ULA', samples_per_step=K).eval()
+        gd.load_state_dict(sd, strict=False)
+        den.plan_for(b)
+        flush.zero_()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        gd.p_sample_loop(b, seed=2)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1)
+        ev = Tc * (1 + K)
+        fl = algorithmic_flops(b.num_edges, b.num_nodes, dims[-1][0])['total']
+        out[key] = dict(workload=desc, timesteps=Tc, scenes_per_gpu=b.num_graphs, nodes=b.num_nodes, edges=b.num_edges, ms_per_step=ms,
+                        ms_per_evaluation=ms / ev, value=b.num_graphs / (ms / 1e3), unit='scenes/s (one GPU, device-timed, 1 step)',
+                        algorithmic_tflops=fl * ev / (ms * 1e-3) / 1e12)
+        den.drop_plans()
+        del den, gd, warm
+    return out
 
 
 def default_math():

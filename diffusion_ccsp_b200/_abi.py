@@ -26,7 +26,7 @@ EXPORTS = [
     'ccsp_plan_set_timing', 'ccsp_plan_get_timing', 'ccsp_plan_h2d_bytes',
     'ccsp_check_solved',
     'ccsp_train_graph_create', 'ccsp_train_graph_destroy', 'ccsp_train_graph_num_edges_of_type', 'ccsp_train_step',
-    'ccsp_adam_step',
+    'ccsp_adam_step', 'ccsp_energy_grad',
 ]
 
 

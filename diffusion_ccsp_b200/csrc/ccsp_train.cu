@@ -139,6 +139,58 @@ struct EncGrads { float *w0, *b0, *w2, *b2; };
 
 }  // namespace
 
+// forward of ConstraintDiffuser on g->xt (denoise_fn.py:466-521): encoders, time term, first layer, decoder -> g->O [2 Epad, P]
+static int forward_pass(CcspTrainGraph *g, const CcspParams *w, const PtrTable &W, const PtrTable &B, int t, SegSrc &in, cudaStream_t st) {
+  const int n = (int)g->n, P = g->P, C = g->C;
+  const int64_t Epad = g->Epad;
+  const int rows2 = (int)(2 * Epad);
+  const int ntab = g->Gr > 0 ? 3 : 2;
+  const EncPtrs ew[3] = {{w->geom_w0, w->geom_b0, w->geom_w2, w->geom_b2}, {w->pose_w0, w->pose_b0, w->pose_w2, w->pose_b2},
+                         {w->grasp_w0, w->grasp_b0, w->grasp_w2, w->grasp_b2}};
+  const float *enc_in[3] = {g->x, g->xt, g->x};
+  const int enc_ld[3] = {g->F, P, g->F}, enc_off[3] = {0, 0, g->grasp_begin}, enc_k[3] = {g->G, P, g->Gr};
+  int rc;
+  for (int tb = 0; tb < ntab; ++tb) {
+    k_enc1_fwd<<<(n * CCSP_HH + 255) / 256, 256, 0, st>>>(enc_in[tb], enc_ld[tb], enc_off[tb], enc_k[tb], n, ew[tb].w0, ew[tb].b0,
+                                                          g->enc_z1[tb], g->enc_a1[tb]);
+    CCSP_LAUNCH_CHECK();
+    LinearFwd p;
+    p.X = g->enc_a1[tb]; p.W = ew[tb].w2; p.bias = ew[tb].b2; p.Z = g->enc_z2[tb]; p.Y = g->enc_e[tb];
+    p.M_ = n; p.N_ = CCSP_H; p.K_ = CCSP_HH;
+    if ((rc = launch_gemm(p, n, CCSP_H, 1, st))) return rc;
+  }
+  k_time_gemv<0><<<4 * CCSP_H / 8, 256, CCSP_H * sizeof(float), st>>>(t, g->freqs, nullptr, w->time_w1, w->time_b1, 4 * CCSP_H, CCSP_H,
+                                                                     g->emb, g->tz1, g->ta1);
+  CCSP_LAUNCH_CHECK();
+  k_time_gemv<1><<<CCSP_H / 8, 256, 4 * CCSP_H * sizeof(float), st>>>(t, g->freqs, g->ta1, w->time_w3, w->time_b3, CCSP_H, 4 * CCSP_H,
+                                                                     nullptr, nullptr, g->temb);
+  CCSP_LAUNCH_CHECK();
+  k_time_bias_fwd<<<C, 512, 0, st>>>(W, B, g->Kin, g->Kseg, g->temb, g->bias);
+  CCSP_LAUNCH_CHECK();
+  std::memset(&in, 0, sizeof(in));
+  {
+    int s = 0;
+    if (g->Gr > 0) { in.base[s] = g->enc_e[2]; in.idx[s] = g->src_i; ++s; }      // grasp_emb[args_1]  (denoise_fn.py:337)
+    in.base[s] = g->enc_e[0]; in.idx[s] = g->src_i; ++s;
+    in.base[s] = g->enc_e[0]; in.idx[s] = g->src_j; ++s;
+    in.base[s] = g->enc_e[1]; in.idx[s] = g->src_i; ++s;
+    in.base[s] = g->enc_e[1]; in.idx[s] = g->src_j; ++s;
+  }
+  if (Epad > 0) {
+    EdgeL1Fwd p;
+    p.in = in; p.W = W; p.tile_type = g->tile_type; p.bias = g->bias; p.Z = g->Z; p.H = g->H;
+    p.Epad = (int)Epad; p.Kseg = g->Kseg; p.Kin = g->Kin;
+    if ((rc = launch_gemm(p, (int)Epad, CCSP_H2, 1, st))) return rc;
+    LinearFwd q;
+    q.X = g->H; q.W = w->dec_w0; q.bias = w->dec_b0; q.Z = g->D1; q.Y = g->A1;
+    q.M_ = rows2; q.N_ = CCSP_HH; q.K_ = CCSP_H;
+    if ((rc = launch_gemm(q, rows2, CCSP_HH, 1, st))) return rc;
+    k_dec2_fwd<<<(rows2 + 255) / 256, 256, 0, st>>>(g->A1, w->dec_w2, w->dec_b2, rows2, P, g->O);
+    CCSP_LAUNCH_CHECK();
+  }
+  return CCSP_OK;
+}
+
 extern "C" {
 
 int ccsp_train_graph_create(const CcspTrainDims *d, const float *x, int64_t n, const int64_t *edge_index, const float *edge_attr,
@@ -317,49 +369,11 @@ int ccsp_train_step(CcspTrainGraph *g, const CcspParams *w, const CcspParams *dw
   }
   int rc;
 
-  // ---- forward ---------------------------------------------------------------------------------------------------------
   k_q_sample<<<(n * P + 255) / 256, 256, 0, st>>>(g->x0, noise, g->mask, n, P, sqrt_alphas_cumprod_t, sqrt_one_minus_alphas_cumprod_t,
                                                   g->noise, g->xt);
   CCSP_LAUNCH_CHECK();
-  for (int tb = 0; tb < ntab; ++tb) {
-    k_enc1_fwd<<<(n * CCSP_HH + 255) / 256, 256, 0, st>>>(enc_in[tb], enc_ld[tb], enc_off[tb], enc_k[tb], n, ew[tb].w0, ew[tb].b0,
-                                                          g->enc_z1[tb], g->enc_a1[tb]);
-    CCSP_LAUNCH_CHECK();
-    LinearFwd p;
-    p.X = g->enc_a1[tb]; p.W = ew[tb].w2; p.bias = ew[tb].b2; p.Z = g->enc_z2[tb]; p.Y = g->enc_e[tb];
-    p.M_ = n; p.N_ = CCSP_H; p.K_ = CCSP_HH;
-    if ((rc = launch_gemm(p, n, CCSP_H, 1, st))) return rc;
-  }
-  k_time_gemv<0><<<4 * CCSP_H / 8, 256, CCSP_H * sizeof(float), st>>>(t, g->freqs, nullptr, w->time_w1, w->time_b1, 4 * CCSP_H, CCSP_H,
-                                                                     g->emb, g->tz1, g->ta1);
-  CCSP_LAUNCH_CHECK();
-  k_time_gemv<1><<<CCSP_H / 8, 256, 4 * CCSP_H * sizeof(float), st>>>(t, g->freqs, g->ta1, w->time_w3, w->time_b3, CCSP_H, 4 * CCSP_H,
-                                                                     nullptr, nullptr, g->temb);
-  CCSP_LAUNCH_CHECK();
-  k_time_bias_fwd<<<C, 512, 0, st>>>(W, B, g->Kin, g->Kseg, g->temb, g->bias);
-  CCSP_LAUNCH_CHECK();
   SegSrc in;
-  std::memset(&in, 0, sizeof(in));
-  {
-    int s = 0;
-    if (g->Gr > 0) { in.base[s] = g->enc_e[2]; in.idx[s] = g->src_i; ++s; }      // grasp_emb[args_1]  (denoise_fn.py:337)
-    in.base[s] = g->enc_e[0]; in.idx[s] = g->src_i; ++s;
-    in.base[s] = g->enc_e[0]; in.idx[s] = g->src_j; ++s;
-    in.base[s] = g->enc_e[1]; in.idx[s] = g->src_i; ++s;
-    in.base[s] = g->enc_e[1]; in.idx[s] = g->src_j; ++s;
-  }
-  if (Epad > 0) {
-    EdgeL1Fwd p;
-    p.in = in; p.W = W; p.tile_type = g->tile_type; p.bias = g->bias; p.Z = g->Z; p.H = g->H;
-    p.Epad = (int)Epad; p.Kseg = g->Kseg; p.Kin = g->Kin;
-    if ((rc = launch_gemm(p, (int)Epad, CCSP_H2, 1, st))) return rc;
-    LinearFwd q;
-    q.X = g->H; q.W = w->dec_w0; q.bias = w->dec_b0; q.Z = g->D1; q.Y = g->A1;
-    q.M_ = rows2; q.N_ = CCSP_HH; q.K_ = CCSP_H;
-    if ((rc = launch_gemm(q, rows2, CCSP_HH, 1, st))) return rc;
-    k_dec2_fwd<<<(rows2 + 255) / 256, 256, 0, st>>>(g->A1, w->dec_w2, w->dec_b2, rows2, P, g->O);
-    CCSP_LAUNCH_CHECK();
-  }
+  if ((rc = forward_pass(g, w, W, B, t, in, st))) return rc;
   const float inv_count = 1.0f / (float)((size_t)n * P);
   k_node_loss<<<(n + 127) / 128, 128, 0, st>>>(g->O, g->node_ptr, g->node_src, g->mask, g->xtail, g->noise, n, P, g->normalize,
                                                 loss_l1, inv_count, grad_scale, g->out, g->err, g->dOut);
@@ -400,7 +414,7 @@ int ccsp_train_step(CcspTrainGraph *g, const CcspParams *w, const CcspParams *dw
     }
     {
       EdgeL1BwdInput p;
-      p.dZ = g->dZ; p.W = W; p.tile_type = g->tile_type; p.dIn = g->dIn; p.Epad = (int)Epad; p.Kseg = g->Kseg; p.Kin = g->Kin;
+      p.dZ = g->dZ; p.W = W; p.tile_type = g->tile_type; p.dIn = g->dIn; p.Epad = (int)Epad; p.Kseg = g->Kseg; p.Kin = g->Kin; p.col0 = 0;
       if ((rc = launch_gemm(p, (int)Epad, g->Kseg, 1, st))) return rc;
     }
   } else {
@@ -441,6 +455,69 @@ int ccsp_train_step(CcspTrainGraph *g, const CcspParams *w, const CcspParams *dw
     k_enc1_bwd<<<CCSP_HH, 256, 0, st>>>(enc_in[tb], enc_ld[tb], enc_off[tb], enc_k[tb], n, g->enc_dz1[tb], eg[tb].w0, eg[tb].b0);
     CCSP_LAUNCH_CHECK();
   }
+  return CCSP_OK;
+}
+
+int ccsp_energy_grad(CcspTrainGraph *g, const CcspParams *w, int32_t t, const float *x, float *energy_out, float *grad_out,
+                     void *stream) {
+  TR_REQUIRE(g && w && x && energy_out && grad_out, "null argument");
+  TR_REQUIRE(t >= 0 && t < (1 << 20), "timestep out of range");
+  TR_REQUIRE(w->geom_w0 && w->pose_w0 && w->dec_w0 && w->time_w1 && w->mlp_w && w->mlp_b, "null weight pointer");
+  TR_REQUIRE(g->Gr == 0 || w->grasp_w0, "grasp encoder pointers missing");
+  cudaStream_t st = (cudaStream_t)stream;
+  CCSP_CUDA_TRY(cudaSetDevice(g->device));
+  const int n = (int)g->n, P = g->P, C = g->C;
+  const int64_t Epad = g->Epad;
+  const int rows2 = (int)(2 * Epad);
+  PtrTable W, B;
+  for (int c = 0; c < MAX_TYPES; ++c) {
+    W.p[c] = c < C ? w->mlp_w[c] : nullptr; B.p[c] = c < C ? w->mlp_b[c] : nullptr;
+    TR_REQUIRE(c >= C || (W.p[c] && B.p[c]), "null mlps pointer");
+  }
+  int rc;
+  CCSP_CUDA_TRY(cudaMemcpyAsync(g->xt, x, (size_t)n * P * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  SegSrc in;
+  if ((rc = forward_pass(g, w, W, B, t, in, st))) return rc;
+  if (Epad == 0) {
+    CCSP_CUDA_TRY(cudaMemsetAsync(energy_out, 0, sizeof(float), st));
+    CCSP_CUDA_TRY(cudaMemsetAsync(grad_out, 0, (size_t)n * P * sizeof(float), st));
+    return CCSP_OK;
+  }
+  // E and dE/do, then back through decoder -> first layer (pose columns only) -> pose encoder, plus the direct -x term
+  float *err = g->dIn;                       // dIn is [Epad, Kseg] >= 2 Epad floats; the error terms are consumed before it is rewritten
+  k_energy_dO<<<(rows2 + 255) / 256, 256, 0, st>>>(g->O, g->xt, g->src_i, g->src_j, n, rows2, P, g->dO, err);
+  CCSP_LAUNCH_CHECK();
+  k_loss_reduce<<<1, 256, 0, st>>>(err, rows2, 1.0f, energy_out);
+  CCSP_LAUNCH_CHECK();
+  k_dD1<<<(unsigned)(((size_t)rows2 * CCSP_HH + 255) / 256), 256, 0, st>>>(g->dO, w->dec_w2, g->D1, rows2, P, g->dD1);
+  CCSP_LAUNCH_CHECK();
+  {
+    LinearBwdInput p;
+    p.dY = g->dD1; p.W = w->dec_w0; p.Zx = g->Z; p.dX = g->dZ; p.M_ = rows2; p.N_ = CCSP_H; p.K_ = CCSP_HH;
+    if ((rc = launch_gemm(p, rows2, CCSP_H, 1, st))) return rc;
+  }
+  {
+    EdgeL1BwdInput p;
+    p.dZ = g->dZ; p.W = W; p.tile_type = g->tile_type; p.dIn = g->dIn; p.Epad = (int)Epad; p.Kseg = CCSP_H2; p.Kin = g->Kin;
+    p.col0 = g->Kseg - CCSP_H2;              // the two pose segments are the last gathered ones (denoise_fn.py:346-354)
+    if ((rc = launch_gemm(p, (int)Epad, CCSP_H2, 1, st))) return rc;
+  }
+  {
+    NodeBwdArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.dIn = g->dIn; a.node_ptr = g->node_ptr; a.node_src = g->node_src; a.Kseg = CCSP_H2; a.ntab = 1;
+    a.seg_of[0][0] = 0; a.seg_of[0][1] = 1;
+    a.z2[0] = g->enc_z2[1]; a.dz2[0] = g->enc_dz2[1];
+    k_node_bwd<<<n, 256, 0, st>>>(a);
+    CCSP_LAUNCH_CHECK();
+  }
+  {
+    LinearBwdInput p;
+    p.dY = g->enc_dz2[1]; p.W = w->pose_w2; p.Zx = g->enc_z1[1]; p.dX = g->enc_dz1[1]; p.M_ = n; p.N_ = CCSP_HH; p.K_ = CCSP_H;
+    if ((rc = launch_gemm(p, n, CCSP_HH, 1, st))) return rc;
+  }
+  k_energy_grad<<<(n * P + 255) / 256, 256, 0, st>>>(g->enc_dz1[1], w->pose_w0, g->dO, g->node_ptr, g->node_src, n, P, grad_out);
+  CCSP_LAUNCH_CHECK();
   return CCSP_OK;
 }
 

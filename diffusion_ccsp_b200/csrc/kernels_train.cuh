@@ -179,10 +179,11 @@ struct EdgeL1BwdInput {
   PtrTable W;
   const int *tile_type;
   float *dIn;
-  int Epad, Kseg, Kin;
+  int Epad, Kseg, Kin;     // Kseg = width of the column window written to dIn (row stride Kseg)
+  int col0;                // first input column of the window (0: all gathered segments; energy form: the pose segments only)
   __device__ void shape(int, int &M, int &N, int &k0, int &k1) const { M = Epad; N = Kseg; k0 = 0; k1 = CCSP_H2; }
   __device__ float a(int, int m, int k) const { return dZ[(size_t)m * CCSP_H2 + k]; }
-  __device__ float b(int, int m0, int k, int n) const { return W.p[tile_type[m0 / TILE_ROWS]][(size_t)k * Kin + n]; }
+  __device__ float b(int, int m0, int k, int n) const { return W.p[tile_type[m0 / TILE_ROWS]][(size_t)k * Kin + col0 + n]; }
   __device__ void c(int, int m, int n, float acc) const { dIn[(size_t)m * Kseg + n] = acc; }
 };
 
@@ -473,6 +474,34 @@ __global__ void __launch_bounds__(256) k_node_bwd(const NodeBwdArgs A) {
     const size_t o = (size_t)v * CCSP_H + col;
     A.dz2[t][o] = acc[t] * dsilu_f(A.z2[t][o]);
   }
+}
+
+// ---- energy form (denoise_fn.py:373-375, 518-521, 539-548): E = sum over edges and both endpoints of |o - x[arg]|^2 ---------------
+// dO[r, :] = dE/do = 2 (o - x[node(r)]);  err[r] = |o - x|^2;  padded rows contribute nothing
+__global__ void k_energy_dO(const float *O, const float *x, const int *src_i, const int *src_j, int n, int rows, int P, float *dO,
+                            float *err) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  const int node = (r & 1) ? src_j[r >> 1] : src_i[r >> 1];
+  float e = 0.f;
+  for (int p = 0; p < P; ++p) {
+    const float d = node < n ? O[(size_t)r * P + p] - x[(size_t)node * P + p] : 0.f;
+    dO[(size_t)r * P + p] = 2.0f * d;
+    e += d * d;
+  }
+  err[r] = e;
+}
+// dE/dx[v, p] = sum_j dz1[v, j] W0[j, p]   (through the pose encoder)   -  sum_{rows at v} dO[row, p]   (the direct -x term)
+__global__ void k_energy_grad(const float *dz1, const float *W0, const float *dO, const int *node_ptr, const int *node_src, int n, int P,
+                              float *grad) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * P) return;
+  const int v = i / P, p = i % P;
+  float s = 0.f;
+  for (int j = 0; j < CCSP_HH; ++j) s = fmaf(dz1[(size_t)v * CCSP_HH + j], W0[j * P + p], s);
+  float d = 0.f;
+  for (int k = node_ptr[v]; k < node_ptr[v + 1]; ++k) d += dO[(size_t)node_src[k] * P + p];
+  grad[i] = s - d;
 }
 
 // ---- Adam (torch.optim.Adam defaults: no weight decay, no amsgrad; ddpm.py:466) ------------------------------------------------

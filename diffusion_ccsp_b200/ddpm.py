@@ -58,9 +58,11 @@ class GaussianDiffusion(nn.Module):
         self.input_mode = denoise_fn.input_mode
         self.num_timesteps = int(timesteps)
         self.loss_type = loss_type
-        if EBM not in (False, None, 'ULA', 'ULA+'):
-            raise NotImplementedError(f'EBM={EBM!r}: only False / ULA / ULA+ are on the accelerated path '
-                                      '(MALA/HMC need the energy form, SURVEY.md §2 #3)')
+        if EBM not in (False, None, 'ULA', 'ULA+', 'MALA', 'HMC'):
+            raise NotImplementedError(f'EBM={EBM!r}: choose False / ULA / ULA+ / MALA / HMC (train_utils.py:92)')
+        if EBM in ('MALA', 'HMC') and not getattr(denoise_fn, 'energy_wrapper', False):
+            raise ValueError(f'EBM={EBM!r} needs the energy form: wrap the denoiser in ComposedEBMDenoiseFn with '
+                             'energy_wrapper=True (train_utils.py:115-116, 283-284)')
         self.EBM = EBM
 
         def to_torch(a):
@@ -150,6 +152,11 @@ class GaussianDiffusion(nn.Module):
         Returns poses [n,P] on the CUDA device (and a list of T+1 tensors when return_history)."""
         assert not self.training                                                    # ddpm.py:328
         den = self.denoise_fn
+        if getattr(den, 'energy_wrapper', False):       # energy form: host-driven MCMC around ccsp_energy_grad (ebm.py)
+            from .ebm import InjectedNoise, sample_loop_energy
+            if noise is not None and not hasattr(noise, 'randn'):
+                noise = InjectedNoise(noise, den.model.cuda_device())
+            return sample_loop_energy(self, batch, return_history=return_history, noise=noise)
         plan = den.plan_for(batch, verify_content=True)
         dev = plan.model.device
         n, P, T = plan.n, self.dims[-1][0], self.num_timesteps

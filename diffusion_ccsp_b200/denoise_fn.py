@@ -48,8 +48,6 @@ class ConstraintDiffuser(nn.Module):
         super().__init__()
         if model != 'Diffusion-CCSP':
             raise NotImplementedError("only model='Diffusion-CCSP' is on the accelerated path (SURVEY.md §2 #6)")
-        if energy_wrapper:
-            raise NotImplementedError('energy_wrapper=True (MALA/HMC energy form) is out of scope (SURVEY.md §2 #3)')
         if hidden_dim != 256:
             raise NotImplementedError('libccsp_b200 kernels are specialised for hidden_dim=256')
         input_mode = input_mode or 'diffuse_pairwise'
@@ -207,9 +205,56 @@ class ConstraintDiffuser(nn.Module):
             store.clear()
 
     # ------------------------------------------------------------------------------------------
+    # analysis path (visualize_energy.py:401-455 pokes at these): eager torch ops over the nn.Linear containers, on whatever
+    # device the parameters live on.  NOT used by forward / sample / the training step.
+    # ------------------------------------------------------------------------------------------
+    def _get_constraint_inputs(self, i, batch, t, emb_dict, edge_index):
+        """denoise_fn.py:313-339: gathered embeddings of all edges of constraint type i.  edge_index is [E, 2] (the reference
+        passes batch.edge_index.T, :508); t a LongTensor([t])."""
+        edges = torch.where(batch.edge_attr == i)[0]
+        args = torch.stack([edge_index[edges][:, 0], edge_index[edges][:, 1]], dim=1)
+        t = t.reshape(-1)[:1]
+        input_dict = {
+            'args': args,
+            'geoms_emb': emb_dict['geoms_emb'][args],
+            'poses_emb': emb_dict['poses_emb'][args],
+            'time_embedding': self.time_mlp(t.unsqueeze(0).expand(edges.shape[0], 1))[:, 0],     # jactorch.add_dim(t, 0, E_i)
+        }
+        if 'robot' in self.input_mode:
+            input_dict['grasp_emb'] = emb_dict['grasp_emb'][args[:, 0]]
+        return input_dict
+
+    def _process_constraint(self, i, input_dict):
+        """denoise_fn.py:341-371: cat([(grasp), geoms, poses, time]) -> mlps[i] -> halves -> pose_decoder; [B, 2, P]."""
+        geom_emb, pose_emb = input_dict['geoms_emb'], input_dict['poses_emb']
+        embeddings = [geom_emb.reshape(geom_emb.shape[0], -1), pose_emb.reshape(pose_emb.shape[0], -1), input_dict['time_embedding']]
+        if 'robot' in self.input_mode:
+            embeddings = [input_dict['grasp_emb']] + embeddings
+        outputs = self.mlps[i](torch.cat(embeddings, dim=-1))
+        outputs = torch.stack([outputs[:, :self.hidden_dim], outputs[:, self.hidden_dim:]], dim=1)
+        return self.pose_decoder(outputs)
+
+    def _compute_energy(self, i, input_dict, poses_in, outputs):
+        """denoise_fn.py:373-375."""
+        return ((outputs - poses_in[input_dict['args']]) ** 2).sum()
+
+    def _add_constraints_outputs(self, i, input_dict, outputs, all_poses_out, all_counts_out=None):
+        """denoise_fn.py:377-389."""
+        args = input_dict['args'].reshape(-1)
+        outputs = outputs.reshape(-1, outputs.shape[-1])
+        all_poses_out.scatter_add_(0, args.unsqueeze(-1).expand(outputs.shape), outputs)
+        if all_counts_out is not None:
+            all_counts_out += torch.bincount(args, minlength=all_poses_out.shape[0]).to(all_counts_out.device)
+        return all_poses_out, all_counts_out
+
+    # ------------------------------------------------------------------------------------------
     def forward(self, poses_in, batch, t, verbose=False, debug=False, tag='EBM', eval=False):
         """denoise_fn.py:453-537 (non-energy branch).  poses_in [n,P]; t: LongTensor([t]) or int.
         Returns the per-node denoising direction [n,P] on the CUDA device."""
+        if tag == 'EBM' and self.energy_wrapper:                  # denoise_fn.py:518-521, 539-548: (gradients, energy)
+            from .ebm import energy_and_gradient
+            tt = int(t.reshape(-1)[0].item()) if torch.is_tensor(t) else int(t)
+            return energy_and_gradient(self, batch, poses_in, tt)
         plan = self.plan_for(batch)
         dev = plan.model.device
         poses = poses_in.detach().to(dev, torch.float32).contiguous()

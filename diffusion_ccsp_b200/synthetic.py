@@ -101,3 +101,16 @@ def make_trained_state_dict(fixture_path: str = None) -> Dict[str, torch.Tensor]
             assert k in sd and tuple(sd[k].shape) == z[k].shape, k
             sd[k] = torch.from_numpy(z[k].astype(np.float32))
     return sd
+
+
+def load_trained_checkpoint(path: str = None) -> Dict[str, torch.Tensor]:
+    """The qualitative-world checkpoint this repo trained ITSELF (scripts/train_fixture.py: GaussianDiffusion.forward ->
+    ccsp_train_step + ccsp_adam_step on the committed 24k-scene pool, no reference code involved), stored in fp16
+    (diffusion_ccsp_b200/data/denoise_fn_qualitative_fp16.npz, 9.15 M parameters) and widened to fp32 here — the fp32 values ARE
+    the checkpoint, for this repo and for the reference alike.  Selected at 15 000 steps: every N = 8 scene samples finite and
+    the N = 4 solved rate is 22 % per try (profiles/train_fixture_r2e.log)."""
+    import os
+    if path is None:
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'data', 'denoise_fn_qualitative_fp16.npz')
+    z = np.load(path)
+    return {k: torch.from_numpy(z[k].astype(np.float32)) for k in z.files if k.startswith('denoise_fn.')}

@@ -234,6 +234,15 @@ int ccsp_train_step(CcspTrainGraph *g, const CcspParams *weights, const CcspPara
                     float sqrt_alphas_cumprod_t, float sqrt_one_minus_alphas_cumprod_t, const float *noise,
                     int32_t loss_l1, float grad_scale, float *loss_out, float *out_recon, void *stream);
 
+/* N4: the energy form of the denoiser.  Replaces: ConstraintDiffuser.forward(tag='EBM') with
+ * energy_wrapper=True (denoise_fn.py:518-521, 539-548) and its wrapper ComposedEBMDenoiseFn (:57-83): the energy
+ * E = sum over edges and both endpoints of |pose_decoder(...) - x[arg]|^2 (_compute_energy, :373-375) and its gradient
+ * dE/dx, which the reference takes with torch.autograd.grad (:550-555) and here is derived analytically (back through the
+ * decoder, the first layer's pose columns and the pose encoder, plus the direct -x term).  No normalisation and no pinning
+ * in this branch (the sampler pins).  x dev [n,P] -> energy_out dev scalar, grad_out dev [n,P].  FP32; asynchronous. */
+int ccsp_energy_grad(CcspTrainGraph *g, const CcspParams *weights, int32_t t, const float *x, float *energy_out,
+                     float *grad_out, void *stream);
+
 /* Replaces: torch.optim.Adam.step for one flat tensor (defaults: no weight decay, no amsgrad; ddpm.py:466): step >= 1 is the
  * 1-based update count.  All pointers dev [count].  Asynchronous on `stream`. */
 int ccsp_adam_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t count, int32_t step,

@@ -42,7 +42,7 @@ def main():
     dims = synthetic.DIMS['qualitative']
     sd = synthetic.make_state_dict(dims, 'qualitative', seed=0)
     tr = create_trainer('qualitative', timesteps=a.timesteps, EBM='ULA', train_dataset=train_pool, train_num_steps=0,
-                        train_batch_size=a.batch, train_lr=a.lr, results_folder=a.out, render_dir=a.out, device='cuda')
+                        train_batch_size=a.batch, train_lr=a.lr, save_and_sample_every=10 ** 9, results_folder=a.out, render_dir=a.out, device='cuda')
     if a.init:
         sd = {k: v.float() for k, v in torch.load(a.init, map_location='cpu').items()}
     tr.model.load_state_dict(sd, strict=False)
@@ -51,6 +51,7 @@ def main():
     log = dict(steps=[], loss=[], solved=[], train_s=[], config=vars(a))
     t_train = 0.0
     done = 0
+    best = None
     while done < a.steps:
         n = min(a.eval_every, a.steps - done)
         tr.train_num_steps = done + n
@@ -64,20 +65,44 @@ def main():
         frac = float(solved.float().mean())
         frac4 = float(checker4(tr.model.sample(eval4, seed=2)).float().mean())
         free = poses[~eval_batch.mask.bool().cuda()]
-        print(f'[fixture] step {done}: loss {tr.loss_log[-1][1]:.5f}  solved N=8 {frac:.3f} N=4 {frac4:.3f}  collisions {(counts[:, 0] > 0).float().mean():.3f} '
-              f'missing {(counts[:, 1] > 0).float().mean():.3f}  max|x| {float(free.abs().max()):.2f}  train {t_train:.1f}s', flush=True)
-        log['steps'].append(done); log['loss'].append(tr.loss_log[-1][1]); log['solved'].append(frac); log.setdefault('solved_n4', []).append(frac4); log['train_s'].append(t_train)
+        finite = float((counts[:, 0] >= 0).float().mean())
+        print(f'[fixture] step {done}: loss {tr.loss_log[-1][1]:.5f}  solved N=8 {frac:.3f} N=4 {frac4:.3f}  finite scenes N=8 {finite:.3f}  '
+              f'collisions {(counts[:, 0] > 0).float().mean():.3f} missing {(counts[:, 1] > 0).float().mean():.3f}  '
+              f'max|x| {float(free[torch.isfinite(free)].abs().max()):.2f}  train {t_train:.1f}s', flush=True)
+        log['steps'].append(done); log['loss'].append(tr.loss_log[-1][1]); log['solved'].append(frac); log.setdefault('solved_n4', []).append(frac4)
+        log.setdefault('finite_n8', []).append(finite); log['train_s'].append(t_train)
+        score = (finite >= 0.99, frac4 + frac)
+        if best is None or score > best[0]:
+            best = (score, done, {k: v.detach().half().cpu() for k, v in tr.model.state_dict().items() if k.startswith('denoise_fn.')})
     os.makedirs(a.out, exist_ok=True)
-    tr.step = done
-    tr.save('fixture')
-    half = {k: v.half() for k, v in tr.model.state_dict().items() if k.startswith('denoise_fn.')}
-    torch.save(half, os.path.join(a.out, 'denoise_fn_fp16.pt'))
-    np.savez_compressed(os.path.join(a.out, 'denoise_fn_fp16.npz'), **{k: v.cpu().numpy() for k, v in half.items()})
+    (fin_ok, sc), best_step, half = best
+    print(f'[fixture] keeping the checkpoint of step {best_step} (N=8 finite: {fin_ok}, solved N=4 + N=8: {sc:.3f})')
+    np.savez_compressed(os.path.join(a.out, 'denoise_fn_fp16.npz'), trained_steps=best_step, **{k: v.numpy() for k, v in half.items()})
+    # the kept checkpoint under both samplers (ULA K=10 = the headline sampler; plain DDPM = EBM False)
+    from diffusion_ccsp_b200.ddpm import GaussianDiffusion
+    from diffusion_ccsp_b200.denoise_fn import ConstraintDiffuser
+    report = {}
+    for ebm in ('ULA', False):
+        den = ConstraintDiffuser(dims=dims, input_mode='qualitative', device='cuda', verbose=False, math='bf16x3')
+        gd = GaussianDiffusion(den, timesteps=a.timesteps, EBM=ebm, samples_per_step=10).eval()
+        gd.load_state_dict({k: v.float() for k, v in half.items()}, strict=False)
+        for name, b, ck in (('N=8', eval_batch, checker), ('N=4', eval4, checker4)):
+            tries = []
+            ok_any = torch.zeros(b.num_graphs, dtype=torch.bool, device='cuda')
+            for k in range(3):
+                s_k, c_k = ck(gd.sample(b, seed=100 + k), return_counts=True)
+                ok_any |= s_k
+                tries.append(float(s_k.float().mean()))
+            report[f'{ebm}/{name}'] = dict(solved_per_try=tries, solved_top3=float(ok_any.float().mean()), finite=float((c_k[:, 0] >= 0).float().mean()))
+            print(f'[fixture] sampler {ebm} {name}: solved per try {tries}  top-3 {float(ok_any.float().mean()):.3f}', flush=True)
+    log['report'] = report
+    log['kept_step'] = best_step
     log['loss_log'] = tr.loss_log
     log['ms_per_step'] = t_train / max(done, 1) * 1e3
     with open(os.path.join(a.out, 'train_log.json'), 'w') as f:
         json.dump(log, f)
-    print(json.dumps(dict(steps=done, final_loss=log['loss'][-1], solved=log['solved'], solved_n4=log['solved_n4'], ms_per_train_step=log['ms_per_step'])))
+    print(json.dumps(dict(steps=done, kept_step=best_step, final_loss=log['loss'][-1], solved=log['solved'], solved_n4=log['solved_n4'],
+                          ms_per_train_step=log['ms_per_step'], report=report)))
 
 
 if __name__ == '__main__':

@@ -27,7 +27,11 @@ MODES = {
     'boxes': ('diffuse_pairwise', False, lambda: scenes.make_batch('boxes', 3, 12, seed=3)),
     'triangles': ('diffuse_pairwise', True, lambda: scenes.make_batch('triangles', 3, 10, seed=4)),
     'robot_box': ('robot_box', False, lambda: scenes.make_batch('robot_box', 3, 6, seed=5)),
+    # the 3-type 'stability_flat' vocabulary (denoise_fn.py:18, 209-210; rows like qualitative: geom 2 + pose 4)
+    'stability': ('stability_flat', False, lambda: scenes.collate([scenes.random_typed_scene(np.random.default_rng(60 + i), 5, 3, 14, 6)
+                                                                   for i in range(3)])),
 }
+ONLY = [a for a in sys.argv[1:] if not a.startswith('--')]      # e.g. `make_golden.py stability`: only these MODES cases
 
 
 def build_reference(input_mode, dims, T, EBM, K, weight_seed):
@@ -70,11 +74,47 @@ def ula_plus_case():
          input_mode='qualitative', triangular=False, **batch_arrays(b))
 
 
+def mode_cases(modes):
+    # ---- single denoiser evaluation per mode (denoise_fn.py:453-537) ----------------------------
+    for case, (mode, tri, factory) in modes.items():
+        dims = synthetic.dims_for(mode, tri)
+        b = factory()
+        m, gd = build_reference(mode, dims, 100, 'ULA', 10, weight_seed=11)
+        rng = np.random.default_rng(77)
+        poses = rng.standard_normal((b.num_nodes, dims[-1][0])).astype(np.float32)
+        outs = []
+        tvals = np.array([0, 37, 99])
+        for t in tvals:
+            with torch.no_grad():
+                o = m(torch.from_numpy(poses.copy()), b, torch.tensor([int(t)]), eval=True)
+            outs.append(o.detach().numpy())
+        save(f'forward_{case}', poses_in=poses, t=tvals, out=np.stack(outs), weight_seed=11,
+             triangular=tri, input_mode=mode, **batch_arrays(b))
+
+    # ---- short trajectories for the other modes + plain DDPM + other K --------------------------
+    for case, (mode, tri, factory) in modes.items():
+        dims = synthetic.dims_for(mode, tri)
+        b = factory()
+        for (T, EBM, K) in ((3, 'ULA', 10), (6, False, 0), (4, 'ULA', 3)):
+            m, gd = build_reference(mode, dims, T, EBM, K if K else 10, weight_seed=21)
+            noise = synthetic.make_noise(T, K, b.num_nodes, dims[-1][0], seed=456)
+            with injected_randn(noise) as inj:
+                out, hist = gd.sample(b, return_history=True)
+            assert inj.calls == 1 + T * (1 + K), (inj.calls, T, K)
+            hist = torch.stack([h.detach() for h in hist]).numpy()
+            tag = f'K{K}' if EBM else 'ddpm'
+            save(f'traj_{case}_T{T}_{tag}', out=out.detach().numpy(), history=hist, T=T, K=K,
+                 EBM=str(EBM), weight_seed=21, noise_seed=456, input_mode=mode, triangular=tri,
+                 **batch_arrays(b))
+
+
 def main():
     torch.set_num_threads(8)
     dfn, ddpm = load_reference()
     if '--ulaplus-only' in sys.argv:
         return ula_plus_case()
+    if ONLY:
+        return mode_cases({k: v for k, v in MODES.items() if k in ONLY})
 
     # ---- schedule tables (ddpm.py:184-226) --------------------------------------------------
     for T in (100, 1000):
@@ -92,21 +132,7 @@ def main():
         pe = m.time_mlp[0](torch.tensor(ts, dtype=torch.long)).numpy()
     save('time_embedding', t=ts, time_mlp=te, pos_emb=pe, weight_seed=0)
 
-    # ---- single denoiser evaluation per mode (denoise_fn.py:453-537) ----------------------------
-    for case, (mode, tri, factory) in MODES.items():
-        dims = synthetic.dims_for(mode, tri)
-        b = factory()
-        m, gd = build_reference(mode, dims, 100, 'ULA', 10, weight_seed=11)
-        rng = np.random.default_rng(77)
-        poses = rng.standard_normal((b.num_nodes, dims[-1][0])).astype(np.float32)
-        outs = []
-        tvals = np.array([0, 37, 99])
-        for t in tvals:
-            with torch.no_grad():
-                o = m(torch.from_numpy(poses.copy()), b, torch.tensor([int(t)]), eval=True)
-            outs.append(o.detach().numpy())
-        save(f'forward_{case}', poses_in=poses, t=tvals, out=np.stack(outs), weight_seed=11,
-             triangular=tri, input_mode=mode, **batch_arrays(b))
+    mode_cases(MODES)
 
     # ---- trajectories: config 1 (qualitative N=4, batch 8, ULA K=10) --------------------------
     b = scenes.qualitative_batch(8, 4)
@@ -121,21 +147,6 @@ def main():
         save(f'traj_qualitative_n4_T{T}', out=out.detach().numpy(), history=hist, T=T, K=10,
              weight_seed=0, noise_seed=123, input_mode='qualitative', triangular=False, **batch_arrays(b))
 
-    # ---- short trajectories for the other modes + plain DDPM + other K --------------------------
-    for case, (mode, tri, factory) in MODES.items():
-        dims = synthetic.dims_for(mode, tri)
-        b = factory()
-        for (T, EBM, K) in ((3, 'ULA', 10), (6, False, 0), (4, 'ULA', 3)):
-            m, gd = build_reference(mode, dims, T, EBM, K if K else 10, weight_seed=21)
-            noise = synthetic.make_noise(T, K, b.num_nodes, dims[-1][0], seed=456)
-            with injected_randn(noise) as inj:
-                out, hist = gd.sample(b, return_history=True)
-            assert inj.calls == 1 + T * (1 + K), (inj.calls, T, K)
-            hist = torch.stack([h.detach() for h in hist]).numpy()
-            tag = f'K{K}' if EBM else 'ddpm'
-            save(f'traj_{case}_T{T}_{tag}', out=out.detach().numpy(), history=hist, T=T, K=K,
-                 EBM=str(EBM), weight_seed=21, noise_seed=456, input_mode=mode, triangular=tri,
-                 **batch_arrays(b))
     ula_plus_case()
 
 

@@ -108,3 +108,44 @@ def test_plan_cache_never_returns_a_plan_of_other_content(monkeypatch):
     batch.x.numpy()[1, 2] += 0.25
     p2 = den.plan_for(batch, verify_content=True)
     assert p2 is not p1 and p1.closed and torch.equal(p2.content[0], batch.x)
+
+
+def test_analysis_methods_match_the_reference():
+    """`_get_constraint_inputs` / `_process_constraint` / `_add_constraints_outputs` (visualize_energy.py:401-455 uses them):
+    composing them the way ConstraintDiffuser.forward does (denoise_fn.py:508-533) reproduces the reference's output."""
+    import numpy as np
+    import torch
+    from diffusion_ccsp_b200 import scenes, synthetic
+    from diffusion_ccsp_b200.denoise_fn import ConstraintDiffuser
+    from oracle import ref_shim
+    if not ref_shim.reference_available():
+        pytest.skip('reference sources not available')
+    dfn, _ = ref_shim.load_reference()
+    for mode, batch in (('qualitative', scenes.qualitative_batch(3, 4)), ('robot_box', scenes.make_batch('robot_box', 2, 4, seed=1))):
+        dims = synthetic.dims_for(mode)
+        sd = {k[len('denoise_fn.'):]: v for k, v in synthetic.make_state_dict(dims, mode, seed=4).items()}
+        ours = ConstraintDiffuser(dims=dims, input_mode=mode, device='cpu', verbose=False)
+        ours.load_state_dict(sd)
+        ref = dfn.ConstraintDiffuser(dims=dims, hidden_dim=256, input_mode=mode, device='cpu', verbose=False)
+        ref.load_state_dict(sd)
+        P = dims[-1][0]
+        poses = torch.from_numpy(np.random.default_rng(0).standard_normal((batch.num_nodes, P)).astype(np.float32))
+        t = torch.tensor([17])
+        with torch.no_grad():
+            want = ref(poses.clone(), batch, t, eval=True)
+            emb = {'geoms_emb': ours.geom_encoder(batch.x[:, :dims[0][0]]), 'poses_emb': ours.pose_encoder(poses)}
+            if 'robot' in mode:
+                emb['grasp_emb'] = ours.grasp_encoder(batch.x[:, dims[1][1]:dims[1][2]])
+            out, cnt = torch.zeros_like(poses), torch.zeros(batch.num_nodes)
+            for i in range(len(ours.constraint_sets)):
+                inp = ours._get_constraint_inputs(i, batch, t, emb, batch.edge_index.T)
+                if inp['args'].shape[0] == 0:
+                    continue
+                o = ours._process_constraint(i, inp)
+                ref_o = ref._process_constraint(i, ref._get_constraint_inputs(i, batch, t, emb, batch.edge_index.T))
+                assert torch.equal(o, ref_o)
+                assert torch.equal(ours._compute_energy(i, inp, poses, o), ref._compute_energy(i, inp, poses, o))
+                out, cnt = ours._add_constraints_outputs(i, inp, o, out, cnt)
+            out = out / torch.sqrt(cnt)[:, None]
+            out[batch.mask.bool()] = batch.x[:, -P:][batch.mask.bool()]
+        assert torch.allclose(out, want, rtol=0, atol=1e-6)

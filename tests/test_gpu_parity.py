@@ -14,16 +14,19 @@ from diffusion_ccsp_b200 import scenes, synthetic
 from diffusion_ccsp_b200.ddpm import GaussianDiffusion
 from diffusion_ccsp_b200.denoise_fn import ConstraintDiffuser
 from oracle import ccsp_oracle as orc
-from tests.util import case_model, golden_names, load_golden, rel_err
+from tests.util import case_model, golden_names, load_golden, rel_err, rel_err_strict
 
 pytestmark = pytest.mark.gpu
 
+# ~5x the maxima measured on B200 (profiles/parity_errors_r2.jsonl; round 1 asserted 20-200x looser bounds).  fwd = one denoiser
+# evaluation, relative to max|ref| with NO floor; traj = T <= 100 trajectories with seeded-init weights (|x| up to 1.6e4, a stress
+# case), relative to max(1, max|x_ref|).
 TOL = {
-    'fp32': dict(fwd=5e-6, traj=2e-5),       # FP32 FMA on CUDA cores
-    'tf32x3': dict(fwd=1e-5, traj=5e-5),     # tcgen05 kind::tf32, 3-term split, FP32 accumulate  (headline mode)
-    'bf16x3': dict(fwd=5e-5, traj=5e-4),     # tcgen05 kind::f16 (bf16), 3-term split
-    'tf32': dict(fwd=5e-3, traj=5e-2),       # single pass, explicitly reduced precision
-    'bf16': dict(fwd=5e-2, traj=5e-1),
+    'fp32': dict(fwd=1.5e-6, traj=4e-6),     # FP32 FMA on CUDA cores                      measured 6.0e-8 (floored) / 6.5e-7
+    'tf32x3': dict(fwd=4e-6, traj=5e-5),     # tcgen05 kind::tf32, 3-term split             measured 1.6e-7 (floored) / 9.2e-6
+    'bf16x3': dict(fwd=5e-6, traj=5e-5),     # tcgen05 kind::f16 (bf16), 3-term split       measured 2.2e-7 (floored) / 8.7e-6   (default mode)
+    'tf32': dict(fwd=3e-4, traj=2e-3),       # single pass, explicitly reduced precision    measured 1.0e-5 / 4.0e-4
+    'bf16': dict(fwd=3e-3, traj=2.5e-2),     #                                              measured 9.9e-5 / 5.2e-3
 }
 MATHS = ['fp32', 'tf32x3', 'bf16x3', 'tf32', 'bf16']
 EXACT_MATHS = ['fp32', 'tf32x3', 'bf16x3']
@@ -61,8 +64,8 @@ def test_forward_vs_reference_golden(name, math):
     m, _ = build(mode, dims, sd, math=math)
     for t, ref in zip(z['t'], z['out']):
         out = m(torch.from_numpy(z['poses_in']), batch, torch.tensor([int(t)]), eval=True).cpu().numpy()
-        record(f'{name}[t={t}]', math, rel_err(out, ref))
-        assert rel_err(out, ref) < TOL[math]['fwd'], (name, t, rel_err(out, ref))
+        record(f'{name}[t={t}]', math, rel_err_strict(out, ref))
+        assert rel_err_strict(out, ref) < TOL[math]['fwd'], (name, t, rel_err_strict(out, ref))
         mk = batch.mask.numpy().astype(bool)
         assert np.array_equal(out[mk], batch.x.numpy()[:, -dims[-1][0]:][mk])     # denoise_fn.py:533, bit-exact
 
@@ -305,6 +308,33 @@ def test_trained_regime_vs_reference_golden(T, math):
     tol = {'fp32': 2e-5, 'tf32x3': 2e-5, 'bf16x3': 5e-5}[math]
     assert err < tol, err
     assert rel_err(torch.stack(hist).cpu().numpy()[::int(z['history_every'])], z['history']) < tol
+
+
+@pytest.mark.parametrize('math', EXACT_MATHS)
+@pytest.mark.parametrize('name', golden_names('big_'))
+def test_full_size_vs_reference_golden(name, math):
+    """Larger goldens from the unmodified reference (tests/golden/make_big_golden.py): 64 scenes x N = 8 x the FULL T = 1000,
+    K = 10 schedule with the checkpoint this repo trained (realistic regime, the benchmarked workload at 1/16 of its batch), and
+    32-scene T = 100 runs of the other three worlds at the configs' object counts (seeded-init weights: stress regime)."""
+    z, batch = load_golden(name)
+    mode = str(z['input_mode'])
+    dims = synthetic.dims_for(mode, bool(z['triangular']))
+    trained = 'weights' in z and str(z['weights']) == 'trained_checkpoint'
+    sd = synthetic.load_trained_checkpoint() if trained else synthetic.make_state_dict(dims, mode, seed=int(z['weight_seed']))
+    T, K = int(z['T']), int(z['K'])
+    _, gd = build(mode, dims, sd, T=T, K=K, math=math)
+    noise = synthetic.make_noise(T, K, batch.num_nodes, dims[-1][0], seed=int(z['noise_seed']))
+    out, hist = gd.sample(batch, return_history=True, noise=noise)
+    out = out.cpu().numpy()
+    hist = torch.stack(hist).cpu().numpy()[z['history_index']]
+    err, err_h = rel_err(out, z['out']), rel_err(hist, z['history'])
+    record(name, math, max(err, err_h))
+    if trained:
+        assert float(np.abs(out).max()) < 3.0                   # the realistic regime really is O(1)
+        tol = {'fp32': 2e-5, 'tf32x3': 3e-5, 'bf16x3': 5e-5}[math]
+    else:
+        tol = TOL[math]['traj']
+    assert err < tol and err_h < tol, (name, err, err_h)
 
 
 # ---------------------------------------------------------------------------------------------------

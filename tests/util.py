@@ -32,3 +32,9 @@ def rel_err(a, b):
     """max|a-b| / max(1, max|b|): the parity measure of SURVEY.md §8c."""
     a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
     return float(np.max(np.abs(a - b)) / max(1.0, float(np.max(np.abs(b)))))
+
+
+def rel_err_strict(a, b):
+    """max|a-b| / max|b| — no floor at 1: what single denoiser evaluations (|out| ~ 0.3) are held to."""
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.max(np.abs(a - b)) / max(float(np.max(np.abs(b))), 1e-30))
