@@ -179,6 +179,8 @@ struct CcspPlan {
   std::vector<cudaEvent_t> ev;    // groups of 4: before l1 | after l1 | after dec | after node
   size_t ev_used = 0;
   CcspTiming timing = {0, 0.0, 0.0, 0.0};
+  cudaStream_t capture_stream = nullptr;
+  cudaGraphExec_t graph_exec = nullptr;   // CCSP_GRAPH=1: the last captured sampling loop (kept alive until the next call / destroy)
 };
 
 // -------------------------------------------------------------------------------------------------
@@ -673,6 +675,8 @@ void ccsp_plan_destroy(CcspPlan *p) {
       if (v[i] == p) { v.erase(v.begin() + i); break; }
   }
   for (cudaEvent_t e : p->ev) cudaEventDestroy(e);
+  if (p->graph_exec) cudaGraphExecDestroy(p->graph_exec);
+  if (p->capture_stream) cudaStreamDestroy(p->capture_stream);
   p->pool.free_all();
   delete p;
   cudaSetDevice(prev);
@@ -743,7 +747,7 @@ int ccsp_sample(CcspPlan *p, const CcspSchedule *s, const CcspNoise *nz, float *
   CCSP_REQUIRE(s->sqrt_recip_alphas_cumprod && s->sqrt_recipm1_alphas_cumprod && s->posterior_mean_coef1 &&
                    s->posterior_mean_coef2 && s->posterior_log_variance_clipped, "null schedule table");
   CCSP_REQUIRE(!s->samples_per_step || (s->ula_grad_scale && s->step_sizes), "ULA tables missing");
-  cudaStream_t st = (cudaStream_t)stream;
+  cudaStream_t user_st = (cudaStream_t)stream, st = user_st;
   CcspModel *m = p->m;
   const int T = s->T;
   const int per = s->ebm_per_steps > 0 ? s->ebm_per_steps : 1;
@@ -773,6 +777,18 @@ int ccsp_sample(CcspPlan *p, const CcspSchedule *s, const CcspNoise *nz, float *
     a.z = zptr(draw); a.seed = nz->seed; a.node_offset = nz->node_offset; a.draw = draw;
     ++draw;
   };
+
+  // Optional (CCSP_GRAPH=1): capture the whole launch sequence into one CUDA graph and replay it.  Measured on B200
+  // (profiles/README.md, round 2): the loop is bound by the kernels' own latency, not by launch overhead.
+  static const bool want_graph = getenv("CCSP_GRAPH") != nullptr;
+  const bool use_graph = want_graph && p->timing_stride == 0;
+  if (use_graph) {
+    if (p->graph_exec) { CCSP_CUDA_TRY(cudaStreamSynchronize(user_st)); cudaGraphExecDestroy(p->graph_exec); p->graph_exec = nullptr; }
+    // the legacy default stream cannot be captured: record on a private stream, replay on the caller's
+    if (!p->capture_stream) CCSP_CUDA_TRY(cudaStreamCreateWithFlags(&p->capture_stream, cudaStreamNonBlocking));
+    st = p->capture_stream;
+    CCSP_CUDA_TRY(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+  }
 
   // x_T = 0.5 * randn, pinned rows <- gt                                   (ddpm.py:273-274)
   NodeArgs a = node_args_base(p);
@@ -810,6 +826,13 @@ int ccsp_sample(CcspPlan *p, const CcspSchedule *s, const CcspNoise *nz, float *
     }
   }
   CCSP_CUDA_TRY(cudaMemcpyAsync(out, p->x, nP * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (use_graph) {
+    cudaGraph_t graph = nullptr;
+    CCSP_CUDA_TRY(cudaStreamEndCapture(st, &graph));
+    CCSP_CUDA_TRY(cudaGraphInstantiate(&p->graph_exec, graph, 0));
+    cudaGraphDestroy(graph);
+    CCSP_CUDA_TRY(cudaGraphLaunch(p->graph_exec, user_st));
+  }
   return CCSP_OK;
 }
 
