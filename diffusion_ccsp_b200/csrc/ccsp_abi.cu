@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -180,6 +181,13 @@ struct CcspPlan {
   size_t ev_used = 0;
   CcspTiming timing = {0, 0.0, 0.0, 0.0};
   cudaStream_t capture_stream = nullptr;
+  // persistent small-shard path (sample_persistent): two side streams, their events, the flag pair, device schedule arrays
+  cudaStream_t ps_node = nullptr, ps_edge = nullptr;
+  cudaEvent_t pe_begin = nullptr, pe_node = nullptr, pe_edge = nullptr;
+  unsigned *p_flags = nullptr;
+  NodeEval *p_sched = nullptr;
+  int *p_eval_t = nullptr;
+  size_t p_sched_cap = 0;
   cudaGraphExec_t graph_exec = nullptr;   // CCSP_GRAPH=1: the last captured sampling loop (kept alive until the next call / destroy)
 };
 
@@ -472,12 +480,160 @@ static int launch_node(CcspPlan *p, const NodeArgs &a, cudaStream_t st) {
   return CCSP_OK;
 }
 
+
+// host-mapped trap word (see kernels_tc.cuh::trap_with)
+static unsigned long long *g_trap_host = nullptr;
+static unsigned long long *g_ptrace_dev = nullptr;      // persistent-mode timeline: [8 events][32 iterations] ns (words 8.. of the block)
+static void ensure_trap_word() {
+  if (g_trap_host) return;
+  if (cudaHostAlloc((void **)&g_trap_host, 8 * (8 + 8 * 32), cudaHostAllocMapped) != cudaSuccess) { g_trap_host = nullptr; return; }
+  std::memset(g_trap_host, 0, 8 * (8 + 8 * 32));
+  unsigned long long *dptr = nullptr;
+  if (cudaHostGetDevicePointer((void **)&dptr, g_trap_host, 0) == cudaSuccess) {
+    cudaMemcpyToSymbol(tc::g_trap_info, &dptr, sizeof(dptr));
+    g_ptrace_dev = dptr + 8;
+  }
+}
+
+// -------------------------------------------------------------------------------------------------------------------------
+// Persistent small-shard path.  When the whole sample fits on the chip at once — every edge unit on its own CTA pair plus all
+// node CTAs, counted in TPCs so that cluster placement cannot be starved: pairs + node_ctas <= num_sms / 2 — the T x (1 + K)
+// loop runs as TWO kernels launched ONCE (k_edge_fused2_tc<PERSIST>, k_node_tc<PERSIST>) on two side streams.  They hand-shake
+// per evaluation through two device counters (release / acquire at gpu scope) instead of 2 launches per evaluation, so barrier
+// and TMEM set-up, table loads and the W2 fetch are paid once per sample and the launch gaps disappear.  Same arithmetic in the
+// same order: results are bit-identical to the launch-per-evaluation path (tests/test_gpu_persistent.py).
+// -------------------------------------------------------------------------------------------------------------------------
+static bool persistent_eligible(const CcspPlan *p, int *pairs_out) {
+  const CcspModel *m = p->m;
+  const char *env = getenv("CCSP_PERSIST");
+  if (env && env[0] == '0') return false;
+  if (m->math != CCSP_MATH_BF16X3 || p->timing_stride > 0 || p->Epad == 0) return false;
+  const int node_ctas = (int)((p->n + 1 + 63) / 64);
+  const int units = (int)(p->Epad / CCSP_TILE_M);
+  const int tpcs = m->num_sms / 2;
+  const int pairs = std::min(units, tpcs - node_ctas);
+  // only while the shard is latency-bound: at most two rounds of units per pair (beyond that the launch-per-evaluation path
+  // amortises its fixed cost and uses all SMs for the edge phase)
+  if (pairs < 1 || (units + pairs - 1) / pairs > 2) return false;
+  *pairs_out = pairs;
+  if (env && env[0] == '1') return true;                 // forced: every shard that fits
+  // default: tiny batches only (both kernels together on at most half of the chip, one unit per pair) — that is where the
+  // measured gain is (profiles/README.md R2.6: -18 % per evaluation at config 1, +-3 % on the 128- and 256-scene shards)
+  return units <= pairs && node_ctas + pairs <= tpcs / 2;
+}
+
+static int sample_persistent(CcspPlan *p, const CcspSchedule *s, const CcspNoise *nz, float *out, float *history, cudaStream_t user_st,
+                             int pairs) {
+  using M = tc::Mode<tc::KIND_BF16, 3>;
+  CcspModel *m = p->m;
+  const int T = s->T;
+  const int per = s->ebm_per_steps > 0 ? s->ebm_per_steps : 1;
+  const size_t nP = (size_t)p->n * m->P;
+  // ---- the schedule of node iterations and edge evaluations, exactly the launch sequence of ccsp_sample -----------------
+  std::vector<NodeEval> sched;
+  std::vector<int> eval_t;
+  sched.reserve((size_t)T * 11 + 1);
+  unsigned draw = 0;
+  {
+    NodeEval e;
+    std::memset(&e, 0, sizeof(e));
+    e.mode = NODE_INIT; e.pin = 1; e.draw = draw++; e.hist_slot = history ? 0 : -1;
+    sched.push_back(e);
+  }
+  for (int j = T - 1; j >= 0; --j) {
+    const int Kt = (s->samples_per_step && (j % per == 0)) ? s->samples_per_step[j] : 0;
+    const int hslot = history ? T - j : -1;
+    NodeEval e;
+    std::memset(&e, 0, sizeof(e));
+    e.mode = NODE_DDPM;
+    e.a = s->sqrt_recip_alphas_cumprod[j]; e.b = s->sqrt_recipm1_alphas_cumprod[j];
+    e.c1 = s->posterior_mean_coef1[j]; e.c2 = s->posterior_mean_coef2[j];
+    e.sigma = (j == 0 ? 0.f : 1.f) * expf(0.5f * s->posterior_log_variance_clipped[j]);
+    e.pin = Kt == 0; e.hist_slot = Kt == 0 ? hslot : -1; e.draw = draw++;
+    sched.push_back(e); eval_t.push_back(j);
+    for (int i = 0; i < Kt; ++i) {
+      std::memset(&e, 0, sizeof(e));
+      e.mode = NODE_ULA; e.gscale = s->ula_grad_scale[j]; e.ss = s->step_sizes[j]; e.std = sqrtf(2.0f * e.ss);
+      e.pin = i == Kt - 1; e.hist_slot = i == Kt - 1 ? hslot : -1; e.draw = draw++;
+      sched.push_back(e); eval_t.push_back(j);
+    }
+  }
+  const int num_evals = (int)eval_t.size();
+  // ---- device resources (kept on the plan) ---------------------------------------------------------------------------------
+  if (!p->ps_node) {
+    CCSP_CUDA_TRY(cudaStreamCreateWithFlags(&p->ps_node, cudaStreamNonBlocking));
+    CCSP_CUDA_TRY(cudaStreamCreateWithFlags(&p->ps_edge, cudaStreamNonBlocking));
+    CCSP_CUDA_TRY(cudaEventCreateWithFlags(&p->pe_begin, cudaEventDisableTiming));
+    CCSP_CUDA_TRY(cudaEventCreateWithFlags(&p->pe_node, cudaEventDisableTiming));
+    CCSP_CUDA_TRY(cudaEventCreateWithFlags(&p->pe_edge, cudaEventDisableTiming));
+    CCSP_CUDA_TRY(p->pool.alloc(&p->p_flags, 64));
+  }
+  if (p->p_sched_cap < sched.size()) {
+    CCSP_CUDA_TRY(cudaStreamSynchronize(user_st));
+    if (p->p_sched) { p->pool.release(p->p_sched); p->pool.release(p->p_eval_t); }
+    CCSP_CUDA_TRY(p->pool.alloc(&p->p_sched, sched.size()));
+    CCSP_CUDA_TRY(p->pool.alloc(&p->p_eval_t, sched.size()));
+    p->p_sched_cap = sched.size();
+  }
+  CCSP_CUDA_TRY(cudaMemcpyAsync(p->p_sched, sched.data(), sched.size() * sizeof(NodeEval), cudaMemcpyHostToDevice, user_st));
+  CCSP_CUDA_TRY(cudaMemcpyAsync(p->p_eval_t, eval_t.data(), eval_t.size() * sizeof(int), cudaMemcpyHostToDevice, user_st));
+  CCSP_CUDA_TRY(cudaMemsetAsync(p->p_flags, 0, 64 * sizeof(unsigned), user_st));
+  CCSP_CUDA_TRY(cudaEventRecord(p->pe_begin, user_st));
+  CCSP_CUDA_TRY(cudaStreamWaitEvent(p->ps_edge, p->pe_begin, 0));
+  CCSP_CUDA_TRY(cudaStreamWaitEvent(p->ps_node, p->pe_begin, 0));
+  ensure_trap_word();
+  const unsigned node_ctas = (unsigned)((p->n + 1 + 63) / 64);
+  unsigned *node_done = p->p_flags, *edge_done = p->p_flags + 32;      // separate 128-byte lines
+  // both functions are loaded before either runs (lazy module loading would otherwise stall the second launch behind the first kernel)
+  CCSP_CUDA_TRY((tc::configure_node_tc_persistent<M>()));
+  // ---- the edge kernel first: its clusters take whole TPCs -------------------------------------------------------------------
+  {
+    tc::FusedArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.pe_split = p->pe_split[1];
+    a.src_i = p->src_i; a.src_j = p->src_j;
+    a.b_blob = m->blob_l1[m->math]; a.w_blob = m->blob_dec[m->math];
+    a.tile_type = p->tile_type;
+    a.num_m_tiles = (int)(p->Epad / CCSP_TILE_M);
+    a.S = p->S; a.tb = m->tb;
+    a.bd1 = m->dec_b1; a.Wd2 = m->dec_w2; a.bd2 = m->dec_b2; a.P = m->P; a.o = p->o;
+    a.num_evals = num_evals; a.eval_t = p->p_eval_t; a.tb_base = m->tb; a.tb_stride = m->C * CCSP_H2;
+    a.node_done = node_done; a.edge_done = edge_done; a.node_ctas = node_ctas;
+    a.trace = getenv("CCSP_PERSIST_TRACE") ? (long long *)g_ptrace_dev : nullptr;
+    CCSP_CUDA_TRY((tc::launch_fused2_persistent<M>(a, pairs, p->ps_edge)));
+    count_launch();
+  }
+  {
+    NodeArgs a = node_args_base(p);
+    a.z = nz->noise; a.seed = nz->seed; a.node_offset = nz->node_offset;
+    a.has_xinit = nz->x_init != nullptr; a.x_in = nz->x_init;
+    a.hist = history;
+    a.sched = p->p_sched; a.num_iters = (int)sched.size(); a.nP = nP;
+    a.node_done = node_done; a.edge_done = edge_done; a.edge_ctas = (unsigned)(2 * pairs);
+    a.trace = getenv("CCSP_PERSIST_TRACE") ? (long long *)g_ptrace_dev : nullptr;
+    CCSP_CUDA_TRY((tc::launch_node_tc_persistent<M>(a, m->blob_pose[m->math], p->ps_node)));
+    count_launch();
+  }
+  CCSP_CUDA_TRY(cudaEventRecord(p->pe_edge, p->ps_edge));
+  CCSP_CUDA_TRY(cudaEventRecord(p->pe_node, p->ps_node));
+  CCSP_CUDA_TRY(cudaStreamWaitEvent(user_st, p->pe_edge, 0));
+  CCSP_CUDA_TRY(cudaStreamWaitEvent(user_st, p->pe_node, 0));
+  CCSP_CUDA_TRY(cudaMemcpyAsync(out, p->x, nP * sizeof(float), cudaMemcpyDeviceToDevice, user_st));
+  return CCSP_OK;
+}
+
 // =================================================================================================
 // extern "C"
 // =================================================================================================
 extern "C" {
 
 const char *ccsp_last_error(void) { return g_last_error.c_str(); }
+/* developer aid: (line or code << 40 | block << 24 | thread) written by the device thread that trapped, 0 if none */
+unsigned long long ccsp_debug_trap_info(void) { return g_trap_host ? g_trap_host[0] : 0ull; }
+/* developer aid (CCSP_PERSIST_TRACE=1): timeline word [event 0..7][iteration 0..31] of the last persistent sample, ns */
+unsigned long long ccsp_debug_persist_trace(int event, int iter) {
+  return (g_trap_host && event >= 0 && event < 8 && iter >= 0 && iter < 32) ? g_trap_host[8 + event * 32 + iter] : 0ull;
+}
 int ccsp_abi_version(void) { return CCSP_ABI_VERSION; }
 uint64_t ccsp_launch_count(void) { return g_launches; }
 void ccsp_reset_launch_count(void) { g_launches = 0; }
@@ -677,6 +833,11 @@ void ccsp_plan_destroy(CcspPlan *p) {
   for (cudaEvent_t e : p->ev) cudaEventDestroy(e);
   if (p->graph_exec) cudaGraphExecDestroy(p->graph_exec);
   if (p->capture_stream) cudaStreamDestroy(p->capture_stream);
+  if (p->ps_node) cudaStreamDestroy(p->ps_node);
+  if (p->ps_edge) cudaStreamDestroy(p->ps_edge);
+  if (p->pe_begin) cudaEventDestroy(p->pe_begin);
+  if (p->pe_node) cudaEventDestroy(p->pe_node);
+  if (p->pe_edge) cudaEventDestroy(p->pe_edge);
   p->pool.free_all();
   delete p;
   cudaSetDevice(prev);
@@ -755,6 +916,10 @@ int ccsp_sample(CcspPlan *p, const CcspSchedule *s, const CcspNoise *nz, float *
   int rc;
   if ((rc = ensure_time_table(m, T, st))) return rc;
   if ((rc = ensure_mode_buffers(p))) return rc;
+  {
+    int pairs = 0;
+    if (persistent_eligible(p, &pairs)) return sample_persistent(p, s, nz, out, history, user_st, pairs);
+  }
 
   // sampled kernel timing: evaluation `ev_idx` is bracketed by events when selected
   long ev_idx = 0;

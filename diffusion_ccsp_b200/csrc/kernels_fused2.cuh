@@ -294,9 +294,13 @@ struct Fused2Cfg {
 
 // TMA = true: operands arrive through tensor maps (A by tile::gather4, weights as 2-D tiles) whose completion is
 // signalled on the leader's barriers directly; TMA = false: cp.async gather + cp.async.bulk + relay lanes.
-template <class M, bool TMA>
+// PERSIST = true: the kernel loops over all A.num_evals evaluations of a sample() (see FusedArgs): barriers, TMEM and tables
+// are set up once, the pipeline counters simply run on, and the kernel boundary is replaced by the node_done / edge_done flags.
+template <class M, bool TMA, bool PERSIST = false>
 __global__ void __launch_bounds__(Fused2Cfg<M>::THREADS, 1)
 k_edge_fused2_tc(const FusedArgs A, const __grid_constant__ PairMaps maps) {
+  static_assert(!(TMA && PERSIST), "the persistent variant uses the cp.async gather");
+  const int n_ev = PERSIST ? A.num_evals : 1;
   using C = Fused2Cfg<M>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -324,7 +328,7 @@ k_edge_fused2_tc(const FusedArgs A, const __grid_constant__ PairMaps maps) {
   const uint32_t smem_base = smem_u32(smem);
   // (Letting the peer's NON-tensor cp.async.bulk complete_tx on the leader's barrier traps on B200: its barrier has to
   // live in the destination CTA.  Hence the relay lanes of the TMA = false variant.)
-  long long *const tr = (A.trace && blockIdx.x == 0) ? A.trace : nullptr;
+  long long *const tr = (!PERSIST && A.trace && blockIdx.x == 0) ? A.trace : nullptr;
 #define TR(role, slot) do { if (tr && it < 8) tr[((role) * 8 + it) * 16 + (slot)] = clock64(); } while (0)
 #define TRP(role, slot) do { if (tr && itp < 8) tr[((role) * 8 + itp) * 16 + (slot)] = clock64(); } while (0)
 
@@ -403,7 +407,15 @@ k_edge_fused2_tc(const FusedArgs A, const __grid_constant__ PairMaps maps) {
     // when all its earlier cp.async have landed), so a thread never waits for data and all NSTAGE1 stages can be
     // in flight; the peer's barrier is forwarded to the leader by the relay lane below.
     uint32_t g = 0, it = 0;
-    pdl_wait();                          // pe_split is written by the preceding node kernel
+    if (!PERSIST) pdl_wait();            // pe_split is written by the preceding node kernel
+    for (int ev = 0; ev < n_ev; ++ev) {
+    if (PERSIST) {                       // ... or by iteration ev of the persistent node kernel (one poller per CTA)
+      if (t == 0) {
+        wait_flag_ge(A.node_done, (unsigned)(ev + 1) * A.node_ctas);
+        if (blockIdx.x == 0) PTRACE(A.trace, 4, ev);
+      }
+      asm volatile("bar.sync 3, 128;" ::: "memory");
+    }
     for (int u = unit0; u < num_units; u += unit_step, ++it) {
       const int m0 = ((u >> 1) * 2 + (int)rank) * SUB_M;
       uint32_t roff[NP];                 // row offsets in 16-byte units (row stride 1 KB: fits 32 bits up to 4 M nodes)
@@ -429,12 +441,14 @@ k_edge_fused2_tc(const FusedArgs A, const __grid_constant__ PairMaps maps) {
       }
     }
     }
+    }
   } else if (warp >= C::WARP_LOAD) {
     REG_DEC();       // one instruction for the whole warpgroup (warps 20-23), then the per-warp roles
     if (warp == C::WARP_LOAD) {
     if (lane == 0) {
       // ============ first-layer weights: this CTA's 128 of the 256 rows of every chunk =================
       uint32_t g = 0;
+      for (int ev = 0; ev < n_ev; ++ev)
       for (int u = unit0; u < num_units; u += unit_step) {
         const int mt = (u >> 1) * 2, slot = u & 1;
         const int grp = __ldg(&A.tile_type[mt]);
@@ -465,6 +479,7 @@ k_edge_fused2_tc(const FusedArgs A, const __grid_constant__ PairMaps maps) {
       // ============ decoder weights: this CTA's 64 of the 128 rows, chunks in GEMM2's consumption order ==
       uint32_t g2 = 0;
       const uint8_t *blob = A.w_blob + rank * C::W_PART;
+      for (int ev = 0; ev < n_ev; ++ev)
       for (int u = unit0; u < num_units; u += unit_step) {
         for (int q = 0; q < 8; ++q, ++g2) {
           const uint32_t s = g2 % C::NW;
@@ -492,6 +507,7 @@ k_edge_fused2_tc(const FusedArgs A, const __grid_constant__ PairMaps maps) {
         // ============ GEMM1 issuer (M = 256 over the pair) =============================================
         uint32_t g = 0, it = 0;
         if (tr) tr[15] = t_entry;          // kernel entry of this thread (slot 15 of MMA1 / unit 0)
+        for (int ev = 0; ev < n_ev; ++ev)
         for (int u = unit0; u < num_units; u += unit_step, ++it) {
           TR(0, 0);
           mbar_wait_cl(tempty1, (it & 1) ^ 1);
@@ -513,6 +529,7 @@ k_edge_fused2_tc(const FusedArgs A, const __grid_constant__ PairMaps maps) {
             umma_commit2(&empty1[s]);
           }
           umma_commit2(tfull1);
+          if (PERSIST && blockIdx.x == 0) PTRACE(A.trace, 5, (int)it);
           TR(0, 4);
         }
       } else if (!TMA) {
@@ -521,6 +538,7 @@ k_edge_fused2_tc(const FusedArgs A, const __grid_constant__ PairMaps maps) {
         uint32_t rfull[C::NSTAGE1];
 #pragma unroll
         for (int s = 0; s < C::NSTAGE1; ++s) rfull[s] = mapa_u32(smem_u32(&full1[s]), 0);
+        for (int ev = 0; ev < n_ev; ++ev)
         for (int u = unit0; u < num_units; u += unit_step) {
           for (int kc = 0; kc < M::NKC1; ++kc, ++g) {
             const uint32_t s = g % C::NSTAGE1;
@@ -535,6 +553,7 @@ k_edge_fused2_tc(const FusedArgs A, const __grid_constant__ PairMaps maps) {
       if (leader) {
         // ============ GEMM2 issuer ======================================================================
         uint32_t g2 = 0, it = 0;
+        for (int ev = 0; ev < n_ev; ++ev)
         for (int u = unit0; u < num_units; u += unit_step, ++it) {
           const uint32_t buf = it & 1;
           TR(1, 0);
@@ -567,6 +586,7 @@ k_edge_fused2_tc(const FusedArgs A, const __grid_constant__ PairMaps maps) {
         uint32_t rfull[C::NW];
 #pragma unroll
         for (int s = 0; s < C::NW; ++s) rfull[s] = mapa_u32(smem_u32(&w_full[s]), 0);
+        for (int ev = 0; ev < n_ev; ++ev)
         for (int u = unit0; u < num_units; u += unit_step) {
           for (int q = 0; q < 8; ++q, ++g2) {
             const uint32_t s = g2 % C::NW;
@@ -594,7 +614,8 @@ k_edge_fused2_tc(const FusedArgs A, const __grid_constant__ PairMaps maps) {
     }
     // ---- epilogue-2 of unit itp (deferred by one unit: GEMM2 had a whole GEMM1 to finish): D2 -> o -------
     auto epi2 = [&](uint32_t itp, size_t rowp, int slotp) {
-      if (itp == 0) pdl_wait();          // o is still being read by the preceding node kernel until it completes
+      if (!PERSIST && itp == 0) pdl_wait();   // o is still being read by the preceding node kernel until it completes
+                                              // (persistent: the gathers of this evaluation already waited for the node iteration)
       const int trole = warp == 0 ? 2 : 3;
       const bool tron = lane == 0 && (warp == 0 || warp == 12);
       const uint32_t buf = itp & 1;
@@ -669,6 +690,9 @@ k_edge_fused2_tc(const FusedArgs A, const __grid_constant__ PairMaps maps) {
     size_t prev_row = 0;
     int prev_slot = 0;
     uint32_t it = 0;
+    for (int ev = 0; ev < n_ev; ++ev) {
+    const float *tb_ev = PERSIST ? A.tb_base + (size_t)__ldg(&A.eval_t[ev]) * A.tb_stride : A.tb;
+    bool first = true;                   // epilogue-2 is deferred by one unit WITHIN an evaluation and drained at its end
     for (int u = unit0; u < num_units; u += unit_step, ++it) {
       const int mt = (u >> 1) * 2 + (int)rank, slot = u & 1;
       const int grp = __ldg(&A.tile_type[mt]);
@@ -686,7 +710,7 @@ k_edge_fused2_tc(const FusedArgs A, const __grid_constant__ PairMaps maps) {
         prefetch_l2_bulk(A.S + (rb * 16 + (size_t)(un & 1) * 8) * 1024, 32768, pol_s);
       }
       float *tbu = tb_s + (it & 1) * 256;
-      if (threadIdx.x < 256) tbu[threadIdx.x] = __ldg(&A.tb[(size_t)grp * CCSP_H2 + slot * 256 + threadIdx.x]);
+      if (threadIdx.x < 256) tbu[threadIdx.x] = __ldg(&tb_ev[(size_t)grp * CCSP_H2 + slot * 256 + threadIdx.x]);
       const int trole = warp == 0 ? 2 : 3;
       const bool tron = lane == 0 && (warp == 0 || warp == 12);
       if (tron) TR(trole, 0);
@@ -694,6 +718,7 @@ k_edge_fused2_tc(const FusedArgs A, const __grid_constant__ PairMaps maps) {
       if (tron) TR(trole, 1);
       // ---- epilogue-1: D1 -> decoder operand chunks -------------------------------------------------
       mbar_wait_cl(tfull1, it & 1);
+      if (PERSIST && blockIdx.x == 0 && threadIdx.x == 0) PTRACE(A.trace, 6, ev);
       if (tron) TR(trole, 2);
       tc_fence_after();
       const uint32_t taddr1 = tmem_base + cg * 64 + ((uint32_t)(quarter * 32) << 16);
@@ -736,10 +761,20 @@ k_edge_fused2_tc(const FusedArgs A, const __grid_constant__ PairMaps maps) {
         if (lane == 0) mbar_arrive_remote(r_a2_full);
         if (tron) TR(trole, 4 + 2 * half);
       }
-      if (it > 0) epi2(it - 1, prev_row, prev_slot);
+      if (!first) epi2(it - 1, prev_row, prev_slot);
+      first = false;
       prev_row = row; prev_slot = slot;
     }
-    if (it > 0) epi2(it - 1, prev_row, prev_slot);
+    if (!first) epi2(it - 1, prev_row, prev_slot);
+    if (PERSIST) {                       // every o row of this CTA for evaluation ev is written: tell the node kernel
+      __threadfence();
+      asm volatile("bar.sync 2, 512;" ::: "memory");
+      if (threadIdx.x == 0) {
+        red_release_gpu_add(A.edge_done, 1u);
+        if (blockIdx.x == 0) PTRACE(A.trace, 7, ev);
+      }
+    }
+    }
   }
 #undef TR
 #undef TRP
@@ -753,6 +788,7 @@ k_edge_fused2_tc(const FusedArgs A, const __grid_constant__ PairMaps maps) {
 
 template <class M, bool TMA>
 cudaError_t launch_fused2_impl(const FusedArgs &a, const PairMaps &maps, int num_sms, cudaStream_t st) {
+  if (a.num_evals != 0) return cudaErrorInvalidValue;      // persistent arguments go through launch_fused2_persistent
   using C = Fused2Cfg<M>;
   static int max_clusters_dev[64] = {};      // per device: function attributes and cluster occupancy
   int dev_ = 0;
@@ -790,6 +826,33 @@ cudaError_t launch_fused2_impl(const FusedArgs &a, const PairMaps &maps, int num
   attrs[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attrs; cfg.numAttrs = 2;
   return cudaLaunchKernelEx(&cfg, k_edge_fused2_tc<M, TMA>, a, maps);
+}
+
+// Persistent variant: `nclusters` CTA pairs stay resident for all a.num_evals evaluations (no PDL attribute: nothing precedes it).
+template <class M>
+cudaError_t launch_fused2_persistent(const FusedArgs &a, int nclusters, cudaStream_t st) {
+  using C = Fused2Cfg<M>;
+  static bool configured_dev[64] = {};
+  int dev_ = 0;
+  cudaGetDevice(&dev_);
+  if (!configured_dev[dev_ & 63]) {
+    cudaError_t e = cudaFuncSetAttribute(k_edge_fused2_tc<M, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    cudaFuncAttributes fa;
+    e = cudaFuncGetAttributes(&fa, k_edge_fused2_tc<M, false, true>);
+    if (e != cudaSuccess) return e;
+    if (fa.numRegs * C::THREADS < C::NUM_EPI * 32 * C::EPI_REGS + (C::THREADS - C::NUM_EPI * 32) * C::AUX_REGS) return cudaErrorLaunchOutOfResources;
+    configured_dev[dev_ & 63] = true;
+  }
+  if (a.num_m_tiles % 2 != 0 || a.num_evals <= 0 || nclusters <= 0 || nclusters > a.num_m_tiles) return cudaErrorInvalidValue;
+  static const PairMaps none = {};
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(nclusters * 2); cfg.blockDim = dim3(C::THREADS); cfg.dynamicSmemBytes = C::SMEM_BYTES; cfg.stream = st;
+  cudaLaunchAttribute attrs[1];
+  attrs[0].id = cudaLaunchAttributeClusterDimension;
+  attrs[0].val.clusterDim.x = 2; attrs[0].val.clusterDim.y = 1; attrs[0].val.clusterDim.z = 1;
+  cfg.attrs = attrs; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, k_edge_fused2_tc<M, false, true>, a, none);
 }
 
 // maps == nullptr selects the cp.async / relay variant

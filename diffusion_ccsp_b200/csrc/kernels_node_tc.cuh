@@ -47,8 +47,10 @@ struct NodeTcCfg {
 // PT: pose width known at compile time (2 boxes, 4 qualitative / triangles, 5 robot; 0 = read A.P at run time).  The
 // kernel runs once per launch from a cold instruction cache with two warps on its critical path, so the code it
 // has to fetch is its run time: a compile-time P removes every `p < P` predicate and the dead component code.
-template <class M, int PT>
-__global__ void __launch_bounds__(NodeTcCfg<M>::THREADS, 1) k_node_tc(const NodeArgs A, const uint8_t *__restrict__ w2_blob) {
+// PERSIST = true: all A.num_iters iterations of a sample() in one launch (see NodeArgs): barriers, TMEM, W2 and the first-layer
+// tables are set up once; the kernel boundary is replaced by the edge_done / node_done flags.
+template <class M, int PT, bool PERSIST = false>
+__global__ void __launch_bounds__(NodeTcCfg<M>::THREADS, 1) k_node_tc(const NodeArgs A0, const uint8_t *__restrict__ w2_blob) {
   using C = NodeTcCfg<M>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -68,9 +70,10 @@ __global__ void __launch_bounds__(NodeTcCfg<M>::THREADS, 1) k_node_tc(const Node
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row0 = blockIdx.x * C::ROWS;
-  const int P = PT ? PT : A.P;
+  const int P = PT ? PT : A0.P;
   const uint32_t smem_base = smem_u32(smem);
-  long long *const tr = (A.trace && blockIdx.x == 1 && (tid == 0 || tid == C::ROW_THREADS)) ? A.trace + (tid == 0 ? 0 : 16) : nullptr;
+  long long *const tr = (!PERSIST && A0.trace && blockIdx.x == 1 && (tid == 0 || tid == C::ROW_THREADS)) ? A0.trace + (tid == 0 ? 0 : 16) : nullptr;
+  unsigned long long *const ptr_ = (PERSIST && blockIdx.x == 0 && tid == 0) ? reinterpret_cast<unsigned long long *>(A0.trace) : nullptr;
 #define NTR(slot) do { if (tr) tr[slot] = clock64(); } while (0)
   NTR(0);
   if (tid == 0) pdl_launch_dependents();
@@ -88,13 +91,25 @@ __global__ void __launch_bounds__(NodeTcCfg<M>::THREADS, 1) k_node_tc(const Node
   if (tid < C::ROW_THREADS) {
     for (int i = tid; i < CCSP_HH * CCSP_MAXP; i += C::ROW_THREADS) {
       const int j = i / CCSP_MAXP, d = i % CCSP_MAXP;
-      w0s[i] = d < P ? __ldg(&A.W0[j * P + d]) : 0.f;
+      w0s[i] = d < P ? __ldg(&A0.W0[j * P + d]) : 0.f;
     }
-    if (tid < CCSP_HH) b0s[tid] = __ldg(&A.b0[tid]);
-    if (tid < CCSP_H) b2s[tid] = __ldg(&A.b2[tid]);
+    if (tid < CCSP_HH) b0s[tid] = __ldg(&A0.b0[tid]);
+    if (tid < CCSP_H) b2s[tid] = __ldg(&A0.b2[tid]);
   }
   const int r = tid & (C::ROWS - 1), part = tid >> 6;         // row threads: node row, 1 of 8 helpers of that row
   const int v = row0 + r;
+  const int n_iters = PERSIST ? A0.num_iters : 1;
+#pragma unroll 1
+  for (int iter = 0; iter < n_iters; ++iter) {
+  NodeArgs A = A0;                       // this iteration's arguments
+  PTRACE(ptr_, 0, iter);
+  if (PERSIST) {
+    const NodeEval E = A0.sched[iter];
+    A.mode = E.mode; A.pin = E.pin; A.a = E.a; A.b = E.b; A.c1 = E.c1; A.c2 = E.c2; A.sigma = E.sigma;
+    A.gscale = E.gscale; A.ss = E.ss; A.std = E.std; A.draw = E.draw;
+    A.z = A0.z ? A0.z + (size_t)E.draw * A0.nP : nullptr;
+    A.hist = (A0.hist && E.hist_slot >= 0) ? A0.hist + (size_t)E.hist_slot * A0.nP : nullptr;
+  }
   if (tid < C::ROW_THREADS) {
     if (part == 1 && v < A.n && !A.z &&
         (A.mode == NODE_DDPM || A.mode == NODE_ULA || (A.mode == NODE_INIT && !A.has_xinit))) {
@@ -139,7 +154,13 @@ __global__ void __launch_bounds__(NodeTcCfg<M>::THREADS, 1) k_node_tc(const Node
       }
     }
   }
-  pdl_wait();                            // o / x / pe are produced (or still read) by the preceding edge kernel
+  if (!PERSIST) {
+    pdl_wait();                          // o / x / pe are produced (or still read) by the preceding edge kernel
+  } else if (iter > 0) {                 // ... or by evaluation iter - 1 of the persistent edge kernel
+    if (tid == 0) wait_flag_ge(A0.edge_done, (unsigned)iter * A0.edge_ctas);
+    __syncthreads();
+    PTRACE(ptr_, 1, iter);
+  }
 
   // ---- phase 1a: the 8 threads of a node fetch its incident decoder outputs in parallel -------------------------
   if (tid < C::ROW_THREADS) {
@@ -154,7 +175,7 @@ __global__ void __launch_bounds__(NodeTcCfg<M>::THREADS, 1) k_node_tc(const Node
       if (P == 4) {
         float4 a[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) if (j < cnt) a[j] = reinterpret_cast<const float4 *>(A.o)[src[j]];
+        for (int j = 0; j < 4; ++j) if (j < cnt) a[j] = __ldcg(reinterpret_cast<const float4 *>(A.o) + src[j]);
 #pragma unroll
         for (int j = 0; j < 4; ++j) if (j < cnt) *reinterpret_cast<float4 *>(dst + j * C::PARTS * EW) = a[j];
       } else {
@@ -162,7 +183,7 @@ __global__ void __launch_bounds__(NodeTcCfg<M>::THREADS, 1) k_node_tc(const Node
         for (int j = 0; j < 4; ++j) if (j < cnt) {
           const float *orow = A.o + (size_t)src[j] * P;
 #pragma unroll
-          for (int p = 0; p < EW; ++p) if (p < P) dst[j * C::PARTS * EW + p] = orow[p];
+          for (int p = 0; p < EW; ++p) if (p < P) dst[j * C::PARTS * EW + p] = __ldcg(orow + p);
         }
       }
     }
@@ -231,7 +252,7 @@ __global__ void __launch_bounds__(NodeTcCfg<M>::THREADS, 1) k_node_tc(const Node
 #pragma unroll 1
             for (; k < k1; ++k) {            // entries beyond the staged window (high-degree nodes)
               const float *orow = A.o + (size_t)A.node_src[k] * P;
-              _Pragma("unroll") for (int p = 0; p < CCSP_MAXP; ++p) if (p < P) eps[p] = __fadd_rn(eps[p], orow[p]);
+              _Pragma("unroll") for (int p = 0; p < CCSP_MAXP; ++p) if (p < P) eps[p] = __fadd_rn(eps[p], __ldcg(orow + p));
             }
             NTR(12);
             if (A.normalize) {
@@ -268,6 +289,7 @@ __global__ void __launch_bounds__(NodeTcCfg<M>::THREADS, 1) k_node_tc(const Node
     for (int p = 0; p < CCSP_MAXP; ++p) xs[r][p] = xn[p];
   }
   NTR(3);
+  PTRACE(ptr_, 2, iter);
   __syncthreads();                       // xs; the scratch (= A operand region) is free again
   NTR(4);
 
@@ -306,7 +328,7 @@ __global__ void __launch_bounds__(NodeTcCfg<M>::THREADS, 1) k_node_tc(const Node
 
   if (tid == C::ROW_THREADS) {
     // ---- phase 2: D[128 x 256] = h . W2^T ------------------------------------------------------------------
-    mbar_wait(bfull, 0);
+    mbar_wait(bfull, 0);               // (later iterations: phase 0 stays complete)
     NTR(7);
     tc_fence_after();
 #pragma unroll
@@ -320,7 +342,7 @@ __global__ void __launch_bounds__(NodeTcCfg<M>::THREADS, 1) k_node_tc(const Node
     // ---- phase 3: warp w <-> TMEM lanes 32 (w & 3).. (only lanes 0..63 hold nodes), columns 64 (w >> 2).. +63 ----
     const int quarter = warp & 3, cg = warp >> 2;
     const int rr = quarter * 32 + lane, vv = row0 + rr;
-    mbar_wait(tfull, 0);
+    mbar_wait(tfull, iter & 1);
     NTR(7);
     tc_fence_after();
     const uint32_t taddr = tmem_base + cg * 64 + ((uint32_t)(quarter * 32) << 16);
@@ -372,7 +394,14 @@ __global__ void __launch_bounds__(NodeTcCfg<M>::THREADS, 1) k_node_tc(const Node
     }
   }
   NTR(10);
-  if (warp == C::ROW_THREADS / 32) tmem_dealloc(tmem_base, 256);
+  if (PERSIST) {                         // x / history / pe of this iteration are written: tell the edge kernel; the staging rows
+    __threadfence();                     // (= next iteration's scratch) are free after the barrier
+    __syncthreads();
+    if (tid == 0) red_release_gpu_add(A0.node_done, 1u);
+    PTRACE(ptr_, 3, iter);
+  }
+  }
+  if (warp == C::ROW_THREADS / 32) tmem_dealloc(*tmem_ptr, 256);
   NTR(11);
 #undef NTR
 }
@@ -397,6 +426,36 @@ cudaError_t launch_node_tc_p(const NodeArgs &a, const uint8_t *w2_blob, cudaStre
   attrs[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attrs; cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, k_node_tc<M, PT>, a, w2_blob);
+}
+
+// Persistent variant (run-time pose width: the code stays hot in the instruction cache anyway), no PDL attribute.
+// (configure = load the function NOW: with lazy module loading the first launch of a kernel can synchronise the device, which
+// would deadlock against the already running persistent edge kernel that is waiting for this one)
+template <class M>
+cudaError_t configure_node_tc_persistent() {
+  using C = NodeTcCfg<M>;
+  static bool configured_dev[64] = {};
+  int dev_ = 0;
+  cudaGetDevice(&dev_);
+  if (!configured_dev[dev_ & 63]) {
+    cudaError_t e = cudaFuncSetAttribute(k_node_tc<M, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    cudaFuncAttributes fa;
+    e = cudaFuncGetAttributes(&fa, k_node_tc<M, 0, true>);
+    if (e != cudaSuccess) return e;
+    configured_dev[dev_ & 63] = true;
+  }
+  return cudaSuccess;
+}
+template <class M>
+cudaError_t launch_node_tc_persistent(const NodeArgs &a, const uint8_t *w2_blob, cudaStream_t st) {
+  using C = NodeTcCfg<M>;
+  cudaError_t e0 = configure_node_tc_persistent<M>();
+  if (e0 != cudaSuccess) return e0;
+  if (a.num_iters <= 0 || !a.sched) return cudaErrorInvalidValue;
+  const unsigned blocks = (unsigned)((a.n + 1 + C::ROWS - 1) / C::ROWS);
+  k_node_tc<M, 0, true><<<blocks, C::THREADS, C::SMEM_BYTES, st>>>(a, w2_blob);
+  return cudaGetLastError();
 }
 
 template <class M>

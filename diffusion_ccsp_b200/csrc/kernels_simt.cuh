@@ -154,6 +154,22 @@ struct NodeArgs {
   int pe_fmt;                    // 0: FP32 [n+1,256]; 1: TF32 split, 2: BF16 split  ([n+1][256 hi | 256 lo], kernels_tc.cuh)
   void *pe;
   long long *trace;              // developer aid (CCSP_NODE_TRACE=1): clock64 at the phase boundaries of CTA 0, else nullptr
+  // persistent mode (k_node_tc<.., PERSIST = true>): the kernel runs ALL num_iters node iterations of a sample() (the init
+  // step + one update per denoiser evaluation) next to the persistent edge kernel; per-iteration arguments come from `sched`
+  const struct NodeEval *sched;  // [num_iters]
+  int num_iters;
+  size_t nP;                     // n * P: stride of the injected draws (z + draw * nP) and of the history slots
+  unsigned *node_done;           // += 1 per CTA and iteration (x and pe of the iteration are written)
+  unsigned *edge_done;           // iteration i >= 1 may start once it reaches i * edge_ctas
+  unsigned edge_ctas;
+};
+
+// per-iteration arguments of the persistent node kernel (what ccsp_sample passes per launch otherwise)
+struct NodeEval {
+  int mode, pin;
+  float a, b, c1, c2, sigma, gscale, ss, std;
+  unsigned int draw;
+  int hist_slot;                 // history slot this iteration writes, or -1
 };
 
 // 64 nodes per block, 512 threads.  Stage 0: one (node, component) pair per thread; stage 1: layer 1 of the

@@ -41,8 +41,18 @@ constexpr int EPI_THREADS = NUM_EPI_WARPS * 32;
 // hanging the GPU.  Release builds spin without a limit: a legitimate stall (debugger, MPS time slice, preemption) must not
 // poison the host's CUDA context.
 constexpr uint32_t SPIN_LIMIT = 1u << 22;
+// Where a trap came from: a host-mapped word (set by the host through ccsp::tc::set_trap_info_ptr) that the trapping thread
+// fills in first — it survives the death of the CUDA context, so the host can still read it (ccsp_debug_trap_info()).
+__device__ unsigned long long *g_trap_info = nullptr;
+__device__ __noinline__ void trap_with(unsigned code) {
+  if (g_trap_info) {
+    g_trap_info[0] = ((unsigned long long)code << 40) | ((unsigned long long)(blockIdx.x & 0xFFFFu) << 24) | (threadIdx.x & 0xFFFFFFu);
+    __threadfence_system();
+  }
+  __trap();
+}
 #ifdef CCSP_DEBUG_SPIN_TRAP
-#define CCSP_SPIN_GUARD(spins) do { if (++(spins) > ::ccsp::tc::SPIN_LIMIT) __trap(); } while (0)
+#define CCSP_SPIN_GUARD(spins) do { if (++(spins) > ::ccsp::tc::SPIN_LIMIT) ::ccsp::tc::trap_with(__LINE__); } while (0)
 #else
 #define CCSP_SPIN_GUARD(spins) do { (void)(spins); } while (0)
 #endif
@@ -728,7 +738,42 @@ struct FusedArgs {
   float *o;                  // [Epad][2][P]
   int dbg;
   long long *trace;          // harness only: clock64 timeline of CTA 0 ([role][unit < 8][16]), else nullptr
+  // persistent mode (k_edge_fused2_tc<.., PERSIST = true>): the kernel stays resident for ALL evaluations of a sample() next to
+  // the persistent node kernel and hand-shakes with it through two device counters instead of kernel boundaries
+  int num_evals;             // denoiser evaluations of the sample
+  const int *eval_t;         // [num_evals] timestep of each evaluation: tb = tb_base + eval_t[ev] * tb_stride
+  const float *tb_base;
+  int tb_stride;
+  unsigned *node_done;       // += 1 per node CTA and node iteration; evaluation ev may gather once it reaches (ev + 1) * node_ctas
+  unsigned *edge_done;       // += 1 per edge CTA and evaluation (all of its o rows written)
+  unsigned node_ctas;
 };
+
+// ---- device-scope flags of the persistent pair of kernels ------------------------------------------------------------
+__device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned *p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_gpu_add(unsigned *p, unsigned v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// persistent-mode timeline (developer aid, CCSP_PERSIST_TRACE=1): trace[event][iteration < 32] in ns of the global timer
+#define PTRACE(buf, event, iter) do { if ((buf) && (iter) < 32) (buf)[(event) * 32 + (iter)] = ::ccsp::tc::global_ns(); } while (0)
+// Bounded on purpose, in every build: the two persistent kernels must be co-resident; if they are not (the launcher's
+// occupancy rule was violated) a trap is the only alternative to a device-wide hang.  2^27 polls x >= 100 ns > 10 s.
+__device__ __forceinline__ void wait_flag_ge(const unsigned *p, unsigned target) {
+  unsigned spins = 0;
+  while ((int)(ld_acquire_gpu_u32(p) - target) < 0) {
+    if (++spins > (1u << 27)) trap_with(900000u + (target & 0xFFFFu));
+    __nanosleep(40);
+  }
+}
 
 // ---------------------------------------------------------------------------------------------------
 // host: pack a row-major FP32 weight block W[n_rows_total, ldw] (nn.Linear layout, K along columns

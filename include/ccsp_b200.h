@@ -104,6 +104,11 @@ typedef struct {
 } CcspNoise;
 
 const char *ccsp_last_error(void);
+/* developer aid: where a device-side trap came from (source line or code << 40 | block << 24 | thread), readable even after the
+ * CUDA context died; 0 = none */
+unsigned long long ccsp_debug_trap_info(void);
+/* developer aid (CCSP_PERSIST_TRACE=1): global-timer timeline of the persistent kernels, [event 0..7][iteration 0..31], ns */
+unsigned long long ccsp_debug_persist_trace(int event, int iter);
 int ccsp_abi_version(void);
 /* Number of kernels launched by this library on the calling thread since the last reset (bench.py's
  * `gpu_launches`). */

@@ -15,7 +15,8 @@ CASES = [('config 1: qualitative N=4, batch 8', 'qualitative', 'qualitative', Fa
          ('config 2: qualitative N=8, batch 1024', 'qualitative', 'qualitative', False, 8, 1024),
          ('config 3: boxes N=12, batch 4096', 'boxes', 'diffuse_pairwise', False, 12, 4096),
          ('config 4: triangles N=10, batch 1024 (8192 / 8 GPUs)', 'triangles', 'diffuse_pairwise', True, 10, 1024),
-         ('config 5: robot boxes N=6, batch 256 (2048 / 8 GPUs)', 'robot_box', 'robot_box', False, 6, 256)]
+         ('config 5: robot boxes N=6, batch 256 (2048 / 8 GPUs)', 'robot_box', 'robot_box', False, 6, 256),
+         ('config 2 strong-scaling shard at 8 GPUs: qualitative N=8, batch 128', 'qualitative', 'qualitative', False, 8, 128)]
 T, K = 40, 10
 for name, kind, mode, tri, n_obj, B in CASES:
     dims = synthetic.dims_for(mode, tri)

@@ -1,0 +1,78 @@
+"""GPU: the persistent small-shard path (two kernels launched once per sample(), hand-shaking through device flags) gives
+bit-identical results to the launch-per-evaluation path — same arithmetic, same order — for Philox and injected noise, with
+history, for every pose width, and falls back by itself when the shard does not fit."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from diffusion_ccsp_b200 import _abi, scenes, synthetic
+from diffusion_ccsp_b200.ddpm import GaussianDiffusion
+from diffusion_ccsp_b200.denoise_fn import ConstraintDiffuser
+
+pytestmark = pytest.mark.gpu
+
+
+def same_bits(a, b):
+    """bit-for-bit equality (NaNs included: short schedules with trained weights can overflow)"""
+    return torch.equal(a.contiguous().view(torch.int32), b.contiguous().view(torch.int32))
+
+
+def run(batch, mode, tri, T, K, persist, EBM='ULA', trained=False, **kw):
+    dims = synthetic.dims_for(mode, tri)
+    sd = synthetic.load_trained_checkpoint() if trained else synthetic.make_state_dict(dims, mode, seed=3)
+    den = ConstraintDiffuser(dims=dims, input_mode=mode, device='cuda', verbose=False, math='bf16x3')
+    gd = GaussianDiffusion(den, timesteps=T, EBM=EBM, samples_per_step=K if K else 10).eval()
+    gd.load_state_dict(sd, strict=False)
+    os.environ['CCSP_PERSIST'] = '1' if persist else '0'
+    try:
+        den.plan_for(batch)                     # the plan's own launches are not what is counted
+        _abi.reset_launch_count()
+        out = gd.sample(batch, **kw)
+        torch.cuda.synchronize()
+        return out, _abi.launch_count()
+    finally:
+        os.environ.pop('CCSP_PERSIST', None)
+
+
+CASES = [('qualitative', False, lambda: scenes.qualitative_batch(8, 4), True),            # config 1
+         ('qualitative', False, lambda: scenes.qualitative_batch(128, 8), True),          # the N = 8 strong-scaling shard
+         ('diffuse_pairwise', False, lambda: scenes.make_batch('boxes', 64, 12, seed=1), False),
+         ('diffuse_pairwise', True, lambda: scenes.make_batch('triangles', 96, 10, seed=2), False),
+         ('robot_box', False, lambda: scenes.make_batch('robot_box', 256, 6, seed=3), False)]   # config 5 shard
+
+
+@pytest.mark.parametrize('case', CASES, ids=['config1', 'n8_shard128', 'boxes64', 'triangles96', 'robot256'])
+def test_persistent_equals_launch_per_evaluation(case):
+    mode, tri, factory, trained = case
+    batch = factory()
+    T, K = 12, 5
+    a, la = run(batch, mode, tri, T, K, persist=False, trained=trained, seed=11)
+    b, lb = run(batch, mode, tri, T, K, persist=True, trained=trained, seed=11)
+    # (+2 when the model's time table is built inside the call)
+    assert la - (1 + 2 * T * (1 + K)) in (0, 2) and lb in (2, 4), (la, lb)     # the persistent path really ran: two launches per sample
+    assert same_bits(a, b)
+    # a second sample on the same plan (flags are reset, barriers re-initialised by the fresh launch)
+    c, _ = run(batch, mode, tri, T, K, persist=True, trained=trained, seed=12)
+    d, _ = run(batch, mode, tri, T, K, persist=False, trained=trained, seed=12)
+    assert same_bits(c, d) and not same_bits(a, c)
+
+
+def test_persistent_history_injected_noise_ddpm_and_ulaplus():
+    batch = scenes.qualitative_batch(16, 4)
+    dims = synthetic.DIMS['qualitative']
+    for EBM, T, K in (('ULA', 6, 3), (False, 9, 0), ('ULA+', 8, 10)):
+        draws = 1 + T + (2 * (4 + 8 + 12 + 16) if EBM == 'ULA+' else T * K)
+        noise = torch.from_numpy(np.random.default_rng(T).standard_normal((draws, batch.num_nodes, 4), dtype=np.float32))
+        (a, ha), _ = run(batch, 'qualitative', False, T, K, persist=False, EBM=EBM, trained=True, noise=noise, return_history=True)
+        (b, hb), lb = run(batch, 'qualitative', False, T, K, persist=True, EBM=EBM, trained=True, noise=noise, return_history=True)
+        assert lb in (2, 4) and same_bits(a, b)
+        assert len(ha) == len(hb) == T + 1 and all(same_bits(x, y) for x, y in zip(ha, hb))
+
+
+def test_large_shards_fall_back_to_the_launch_per_evaluation_path():
+    batch = scenes.qualitative_batch(1024, 8)
+    out, launches = run(batch, 'qualitative', False, 2, 2, persist=True, trained=True, seed=5)
+    assert launches - (1 + 2 * 2 * 3) in (0, 2)                       # 645 units do not fit next to 145 node CTAs
+    assert bool(torch.isfinite(out).all())
