@@ -267,7 +267,7 @@ def make_batch(kind: str, num_scenes: int, n_obj: int, seed: int = 0) -> SceneBa
 
 # -------------------------------------------------------------------------------------
 # RandomSplitQualitativeWorld scenes: committed fixtures (diffusion_ccsp_b200/data/) generated with the reference's own
-# scene generator + qualitative labeller (tests/golden/make_scenes.py, scripts/make_train_pool.py); tiled to any batch.
+# scene generator + qualitative labeller (tests/golden/make_scenes.py, tests/golden/make_train_pool.py); tiled to any batch.
 # -------------------------------------------------------------------------------------
 _FIXTURE_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'data')
 
@@ -294,7 +294,7 @@ def qualitative_batch(num_scenes: int, n_obj: int = 8, seed: int = 0,
 
 
 def qualitative_train_pool(path: Optional[str] = None) -> SceneBatch:
-    """The committed TRAINING pool (24 000 RandomSplitQualitativeWorld scenes with 2..8 tiles, scripts/make_train_pool.py):
+    """The committed TRAINING pool (24 000 RandomSplitQualitativeWorld scenes with 2..8 tiles, tests/golden/make_train_pool.py):
     disjoint draws from the evaluation fixtures, stored with scene-local edge ids."""
     z = np.load(path or os.path.join(_FIXTURE_DIR, 'scenes_qualitative_train.npz'))
     ncount, ecount = z['nodes_per_scene'].astype(np.int64), z['edges_per_scene'].astype(np.int64)

@@ -36,7 +36,7 @@ def main():
     ap.add_argument('--lr', type=float, default=5e-4)
     a = ap.parse_args()
     torch.manual_seed(a.seed)
-    train_pool = scenes.qualitative_train_pool()                      # 24 000 scenes, 2..8 tiles (scripts/make_train_pool.py)
+    train_pool = scenes.qualitative_train_pool()                      # 24 000 scenes, 2..8 tiles (tests/golden/make_train_pool.py)
     eval_batch = scenes.qualitative_batch(a.eval_scenes, 8)           # evaluation fixtures: disjoint draws
     eval4 = scenes.qualitative_batch(64, 4)
     dims = synthetic.DIMS['qualitative']

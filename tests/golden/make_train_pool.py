@@ -3,7 +3,7 @@
 labeller (the same recipe as tests/golden/make_scenes.py: envs/builders.py:10-52 + envs/data_utils.py:427-621, 408-415 through
 oracle/ref_shim.py), stored compactly under diffusion_ccsp_b200/data/ so that the repo can train its own checkpoint anywhere.
 
-    python scripts/make_train_pool.py [--scenes 24000]
+    python tests/golden/make_train_pool.py [--scenes 24000]
 
 Scene sizes are mixed (2..8 tiles; the reference trains on mixed sizes too, train_utils.py:153).  Seeds differ from the test
 fixtures (tests/golden/scenes_qualitative_n*.npz), so the pools are disjoint draws.
@@ -15,7 +15,7 @@ import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, 'tests', 'golden'))
 import make_scenes as ms  # noqa: E402

@@ -1,10 +1,10 @@
 #!/usr/bin/env python
-"""Does a checkpoint sample stably?  Our CUDA sampler (bf16x3 and fp32) and, when staged, the unmodified reference on the CPU, on
+"""TEST TOOLING (may load the staged reference through oracle/ref_shim.py).  Does a checkpoint sample stably?  Our CUDA sampler (bf16x3 and fp32) and, when staged, the unmodified reference on the CPU, on
 the same few scenes with the same injected noise: max|x| along the trajectory and the first timestep that goes non-finite."""
 import argparse, os, sys, time
 import numpy as np
 import torch
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from diffusion_ccsp_b200 import scenes, synthetic
 from diffusion_ccsp_b200.ddpm import GaussianDiffusion
