@@ -52,6 +52,7 @@ class Trainer(object):
         self.opt = None                                # train.Adam, created on first use (needs the parameters on the GPU)
         self.step = 0
         self.loss_log = []
+        self.lr_schedule = None                        # optional callable step -> learning rate (the reference trains at a constant rate)
 
     # ---- checkpoints (ddpm.py:496-514) --------------------------------------------------------------
     def save(self, milestone):
@@ -100,6 +101,8 @@ class Trainer(object):
                 self.loss_log.append((self.step, mean))
                 print(f"Step: {self.step} | lr: {opt.param_groups[0]['lr']}\tloss={mean:.6f}")
                 window = []
+            if self.lr_schedule is not None:
+                opt.param_groups[0]['lr'] = float(self.lr_schedule(self.step))
             opt.step()
             opt.zero_grad()
             if self.step % self.save_and_sample_every == (self.save_and_sample_every - 1):

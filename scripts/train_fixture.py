@@ -34,9 +34,16 @@ def main():
     ap.add_argument('--seed', type=int, default=0)
     ap.add_argument('--init', default=None, help='state dict (.pt) to start from')
     ap.add_argument('--lr', type=float, default=5e-4)
+    ap.add_argument('--max-tiles', type=int, default=8, help='train only on scenes with at most this many tiles (the reference trains on 2-5)')
+    ap.add_argument('--cosine', action='store_true', help='cosine decay of the learning rate to 2 % of --lr over --steps (the reference trains at a constant rate)')
     a = ap.parse_args()
     torch.manual_seed(a.seed)
     train_pool = scenes.qualitative_train_pool()                      # 24 000 scenes, 2..8 tiles (tests/golden/make_train_pool.py)
+    if a.max_tiles < 8:
+        off = train_pool.scene_node_ranges()
+        keep = np.where(np.diff(off) - 1 <= a.max_tiles)[0]
+        train_pool = scenes._gather_scenes_fast(train_pool, keep)
+        print(f'[fixture] training on {train_pool.num_graphs} scenes with <= {a.max_tiles} tiles', flush=True)
     eval_batch = scenes.qualitative_batch(a.eval_scenes, 8)           # evaluation fixtures: disjoint draws
     eval4 = scenes.qualitative_batch(64, 4)
     dims = synthetic.DIMS['qualitative']
@@ -56,6 +63,10 @@ def main():
         n = min(a.eval_every, a.steps - done)
         tr.train_num_steps = done + n
         torch.cuda.synchronize(); t0 = time.time()
+        if a.cosine:
+            import math
+            total = a.steps
+            tr.lr_schedule = lambda step: a.lr * (0.02 + 0.98 * 0.5 * (1 + math.cos(math.pi * min(step, total) / total)))
         tr.train(log_every=max(n // 4, 1), evaluate=False)
         torch.cuda.synchronize(); t_train += time.time() - t0
         done += n
@@ -68,7 +79,7 @@ def main():
         finite = float((counts[:, 0] >= 0).float().mean())
         print(f'[fixture] step {done}: loss {tr.loss_log[-1][1]:.5f}  solved N=8 {frac:.3f} N=4 {frac4:.3f}  finite scenes N=8 {finite:.3f}  '
               f'collisions {(counts[:, 0] > 0).float().mean():.3f} missing {(counts[:, 1] > 0).float().mean():.3f}  '
-              f'max|x| {float(free[torch.isfinite(free)].abs().max()):.2f}  train {t_train:.1f}s', flush=True)
+              f'max|x| {float(free[torch.isfinite(free)].abs().max()) if bool(torch.isfinite(free).any()) else float("nan"):.2f}  train {t_train:.1f}s', flush=True)
         log['steps'].append(done); log['loss'].append(tr.loss_log[-1][1]); log['solved'].append(frac); log.setdefault('solved_n4', []).append(frac4)
         log.setdefault('finite_n8', []).append(finite); log['train_s'].append(t_train)
         score = (finite >= 0.99, frac4 + frac)

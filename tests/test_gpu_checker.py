@@ -143,3 +143,24 @@ def test_full_batch_sampler_output_is_checked_in_one_launch():
     s_ref, c_ref, m_ref = chk.check_batch(poses.cpu().numpy(), batch, (2, 6))
     assert np.array_equal(solved.cpu().numpy(), s_ref)
     assert np.array_equal(counts.cpu().numpy()[:, 0], c_ref) and np.array_equal(counts.cpu().numpy()[:, 1], m_ref)
+
+
+def test_scene_and_edge_order_do_not_matter():
+    """per-scene verdicts and counts are invariant under the position of the scene in the batch and under the order of its edges"""
+    rng = np.random.default_rng(9)
+    batch = scenes.qualitative_batch(96, 8, seed=4)
+    poses = perturbed(batch, QDIMS, rng, 0.004)
+    s0, c0 = gpu_check(batch, poses, QDIMS, 'qualitative')
+    # scenes in another order
+    order = rng.permutation(batch.num_graphs)
+    off = batch.scene_node_ranges()
+    b2 = scenes.take_scenes(batch, order)
+    p2 = np.concatenate([poses[off[i]:off[i + 1]] for i in order])
+    s2, c2 = gpu_check(b2, p2, QDIMS, 'qualitative')
+    assert np.array_equal(s2, s0[order]) and np.array_equal(c2, c0[order])
+    # edges in another order (the scene id of every edge travels with it)
+    perm = rng.permutation(batch.num_edges)
+    b3 = scenes.SceneBatch(batch.x, batch.edge_index[:, perm], batch.edge_attr[perm], batch.mask, batch.x_extract, batch.edge_extract[perm])
+    s3, c3 = gpu_check(b3, poses, QDIMS, 'qualitative')
+    assert np.array_equal(s3, s0) and np.array_equal(c3, c0)
+    assert 0 < s0.sum() < s0.size

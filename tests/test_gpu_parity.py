@@ -335,6 +335,43 @@ def test_full_size_vs_reference_golden(name, math):
     assert err < tol and err_h < tol, (name, err, err_h)
 
 
+def test_benchmarked_workload_full_size_vs_reference_prefix_and_fp32():
+    """The benchmarked workload itself — config 2 at its full batch (1 024 scenes, 9 216 nodes, 80 980 edges), T = 1000, K = 10, the
+    trained checkpoint — with injected noise: (1) scenes are independent, so the first 64 scenes must reproduce the UNMODIFIED
+    reference's golden for those scenes (same noise rows); (2) the default bf16x3 tensor-core path must agree with the FP32
+    CUDA-core path on all 1 024 scenes."""
+    z, small = load_golden('big_qualitative_n8_T1000')
+    dims = synthetic.DIMS['qualitative']
+    sd = synthetic.load_trained_checkpoint()
+    T, K = int(z['T']), int(z['K'])
+    batch = scenes.qualitative_batch(1024, 8)
+    n_small = small.num_nodes
+    assert torch.equal(batch.x[:n_small], small.x) and batch.num_nodes == 9216
+    g = torch.Generator(device='cuda').manual_seed(5)
+    noise = torch.randn((1 + T * (1 + K), batch.num_nodes, 4), device='cuda', generator=g)
+    noise[:, :n_small] = synthetic.make_noise(T, K, n_small, 4, seed=int(z['noise_seed'])).cuda()
+    outs = {}
+    for math in ('bf16x3', 'fp32'):
+        _, gd = build('qualitative', dims, sd, T=T, K=K, math=math)
+        outs[math] = gd.sample(batch, noise=noise).cpu().numpy()
+        gd.denoise_fn.drop_plans()
+    for math, out in outs.items():
+        err = rel_err(out[:n_small], z['out'])
+        record('benchmarked_workload_prefix_vs_reference', math, err)
+        assert err < {'fp32': 2e-5, 'bf16x3': 5e-5}[math], (math, err)
+    # all 1 024 scenes: compare scene by scene; the rare scene that the sampler drives off to 1e30+ (an unstable trajectory, the
+    # reference does the same: DESIGN 4.7) amplifies rounding differences without bound and is excluded, but must be rare
+    sid = batch.x_extract.numpy().astype(np.int64)
+    with np.errstate(invalid='ignore'):
+        big = np.zeros(1024, bool)
+        np.logical_or.at(big, sid, ~(np.abs(outs['fp32']).max(axis=1) < 10.0))
+    keep = ~big[sid]
+    assert big.mean() < 0.01, big.mean()
+    err = rel_err(outs['bf16x3'][keep], outs['fp32'][keep])
+    record('benchmarked_workload_bf16x3_vs_fp32', 'bf16x3', err)
+    assert err < 5e-5, err
+
+
 # ---------------------------------------------------------------------------------------------------
 # BASELINE.json configs 3-5 at their full per-GPU batch sizes: size-independent properties
 # ---------------------------------------------------------------------------------------------------
