@@ -359,6 +359,7 @@ static int launch_edge_pair(CcspPlan *p, const float *tb, cudaStream_t st) {
   a.num_m_tiles = (int)(p->Epad / CCSP_TILE_M);
   a.S = p->S; a.tb = tb;
   a.bd1 = m->dec_b1; a.Wd2 = m->dec_w2; a.bd2 = m->dec_b2; a.P = m->P; a.o = p->o;
+  a.pad_row_plus1 = (int)p->n + 1;
   CCSP_CUDA_TRY((tc::launch_fused2_tc<M>(a, m->num_sms, st)));
   count_launch();
   return CCSP_OK;
@@ -486,8 +487,8 @@ static unsigned long long *g_trap_host = nullptr;
 static unsigned long long *g_ptrace_dev = nullptr;      // persistent-mode timeline: [8 events][32 iterations] ns (words 8.. of the block)
 static void ensure_trap_word() {
   if (g_trap_host) return;
-  if (cudaHostAlloc((void **)&g_trap_host, 8 * (8 + 8 * 32), cudaHostAllocMapped) != cudaSuccess) { g_trap_host = nullptr; return; }
-  std::memset(g_trap_host, 0, 8 * (8 + 8 * 32));
+  if (cudaHostAlloc((void **)&g_trap_host, 8 * (8 + 12 * 32), cudaHostAllocMapped) != cudaSuccess) { g_trap_host = nullptr; return; }
+  std::memset(g_trap_host, 0, 8 * (8 + 12 * 32));
   unsigned long long *dptr = nullptr;
   if (cudaHostGetDevicePointer((void **)&dptr, g_trap_host, 0) == cudaSuccess) {
     cudaMemcpyToSymbol(tc::g_trap_info, &dptr, sizeof(dptr));
@@ -506,7 +507,7 @@ static void ensure_trap_word() {
 static bool persistent_eligible(const CcspPlan *p, int *pairs_out) {
   const CcspModel *m = p->m;
   const char *env = getenv("CCSP_PERSIST");
-  if (env && env[0] == '0') return false;
+  if (!env || env[0] == '0') return false;
   if (m->math != CCSP_MATH_BF16X3 || p->timing_stride > 0 || p->Epad == 0) return false;
   const int node_ctas = (int)((p->n + 1 + 63) / 64);
   const int units = (int)(p->Epad / CCSP_TILE_M);
@@ -516,10 +517,11 @@ static bool persistent_eligible(const CcspPlan *p, int *pairs_out) {
   // amortises its fixed cost and uses all SMs for the edge phase)
   if (pairs < 1 || (units + pairs - 1) / pairs > 2) return false;
   *pairs_out = pairs;
-  if (env && env[0] == '1') return true;                 // forced: every shard that fits
-  // default: tiny batches only (both kernels together on at most half of the chip, one unit per pair) — that is where the
-  // measured gain is (profiles/README.md R2.6: -18 % per evaluation at config 1, +-3 % on the 128- and 256-scene shards)
-  return units <= pairs && node_ctas + pairs <= tpcs / 2;
+  // Opt-in only (CCSP_PERSIST=1).  Measured on B200 (profiles/README.md R2.6): once padded rows stopped hammering the zero row
+  // (cp.async zero-fill), the persistent pair is no faster than two launches per evaluation on any shard size — the
+  // per-evaluation floor is the dependent chain inside the phases, not launch overhead — so the default stays with the path
+  // that needs no co-residency guarantee.
+  return env && env[0] == '1';
 }
 
 static int sample_persistent(CcspPlan *p, const CcspSchedule *s, const CcspNoise *nz, float *out, float *history, cudaStream_t user_st,
@@ -597,6 +599,7 @@ static int sample_persistent(CcspPlan *p, const CcspSchedule *s, const CcspNoise
     a.num_m_tiles = (int)(p->Epad / CCSP_TILE_M);
     a.S = p->S; a.tb = m->tb;
     a.bd1 = m->dec_b1; a.Wd2 = m->dec_w2; a.bd2 = m->dec_b2; a.P = m->P; a.o = p->o;
+  a.pad_row_plus1 = (int)p->n + 1;
     a.num_evals = num_evals; a.eval_t = p->p_eval_t; a.tb_base = m->tb; a.tb_stride = m->C * CCSP_H2;
     a.node_done = node_done; a.edge_done = edge_done; a.node_ctas = node_ctas;
     a.trace = getenv("CCSP_PERSIST_TRACE") ? (long long *)g_ptrace_dev : nullptr;
@@ -632,7 +635,7 @@ const char *ccsp_last_error(void) { return g_last_error.c_str(); }
 unsigned long long ccsp_debug_trap_info(void) { return g_trap_host ? g_trap_host[0] : 0ull; }
 /* developer aid (CCSP_PERSIST_TRACE=1): timeline word [event 0..7][iteration 0..31] of the last persistent sample, ns */
 unsigned long long ccsp_debug_persist_trace(int event, int iter) {
-  return (g_trap_host && event >= 0 && event < 8 && iter >= 0 && iter < 32) ? g_trap_host[8 + event * 32 + iter] : 0ull;
+  return (g_trap_host && event >= 0 && event < 12 && iter >= 0 && iter < 32) ? g_trap_host[8 + event * 32 + iter] : 0ull;
 }
 int ccsp_abi_version(void) { return CCSP_ABI_VERSION; }
 uint64_t ccsp_launch_count(void) { return g_launches; }

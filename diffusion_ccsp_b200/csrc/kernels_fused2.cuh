@@ -419,12 +419,18 @@ k_edge_fused2_tc(const FusedArgs A, const __grid_constant__ PairMaps maps) {
     for (int u = unit0; u < num_units; u += unit_step, ++it) {
       const int m0 = ((u >> 1) * 2 + (int)rank) * SUB_M;
       uint32_t roff[NP];                 // row offsets in 16-byte units (row stride 1 KB: fits 32 bits up to 4 M nodes)
+      uint32_t live = 0;                 // bit p: row p of this thread is a real edge
 #pragma unroll 1
       for (int kc = 0; kc < M::NKC1; ++kc, ++g) {
         if (kc == 0 || kc == M::NKC1 / 2) {
           const int *idx = kc == 0 ? A.src_i : A.src_j;
+          live = 0;
 #pragma unroll
-          for (int p = 0; p < NP; ++p) roff[p] = (uint32_t)__ldg(&idx[m0 + r0 + RPP * p]) * (M::PE_ROW_BYTES / 16);
+          for (int p = 0; p < NP; ++p) {
+            const int ix = __ldg(&idx[m0 + r0 + RPP * p]);
+            roff[p] = (uint32_t)ix * (M::PE_ROW_BYTES / 16);
+            live |= (ix + 1 != A.pad_row_plus1 ? 1u : 0u) << p;      // padded rows are zero-filled without touching memory
+          }
         }
         const uint32_t s = g % C::NSTAGE1;
         mbar_wait(&empty1[s], ((g / C::NSTAGE1) & 1) ^ 1);
@@ -434,7 +440,7 @@ k_edge_fused2_tc(const FusedArgs A, const __grid_constant__ PairMaps maps) {
           const uint32_t st = smem_base + s * C::STAGE1 + part * PART;
 #pragma unroll
           for (int p = 0; p < NP; ++p)
-            cp_async16(st + sw64_off(r0 + RPP * p, q), A.pe_split + (size_t)roff[p] * 16 + koff);
+            cp_async16_zfill(st + sw64_off(r0 + RPP * p, q), A.pe_split + (size_t)roff[p] * 16 + koff, ((live >> p) & 1u) ? 16u : 0u);
         }
         cp_async_arrive_noinc(&full1[s]);
         if (t == 0) TR(7, kc);
@@ -517,6 +523,7 @@ k_edge_fused2_tc(const FusedArgs A, const __grid_constant__ PairMaps maps) {
           for (int kc = 0; kc < M::NKC1; ++kc, ++g) {
             const uint32_t s = g % C::NSTAGE1;
             if (!ready) mbar_wait_cl(&full1[s], (g / C::NSTAGE1) & 1);
+            if (PERSIST && blockIdx.x == 0 && ev == 5) PTRACE(A.trace, 8, kc);
             if (kc == 0) TR(0, 2);
             if (kc == 8) TR(0, 3);
             tc_fence_after();
@@ -621,6 +628,7 @@ k_edge_fused2_tc(const FusedArgs A, const __grid_constant__ PairMaps maps) {
       const uint32_t buf = itp & 1;
       if (tron) TRP(trole, 7);
       mbar_wait_cl(&tfull2[buf], (itp >> 1) & 1);
+      if (PERSIST && blockIdx.x == 0 && threadIdx.x == 0) PTRACE(A.trace, 9, 3 + (int)(itp & 3));
       if (tron) TRP(trole, 8);
       tc_fence_after();
       const uint32_t taddr2 = tmem_base + C::D2_COL + buf * C::NT2 + cg * 32 + ((uint32_t)(quarter * 32) << 16);
@@ -726,6 +734,7 @@ k_edge_fused2_tc(const FusedArgs A, const __grid_constant__ PairMaps maps) {
       tmem_ld32(taddr1, vall);
       tmem_ld32(taddr1 + 32, vall + 32);
       tc_fence_before();                             // D1 fully in registers: GEMM1 of the next unit may overwrite it
+      if (PERSIST && blockIdx.x == 0 && threadIdx.x == 0 && ev == 5) PTRACE(A.trace, 9, 0);
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(r_tempty1);
 #pragma unroll
@@ -759,6 +768,7 @@ k_edge_fused2_tc(const FusedArgs A, const __grid_constant__ PairMaps maps) {
         fence_proxy_async();                         // chunk complete: publish to the async proxy, tell the leader
         __syncwarp();
         if (lane == 0) mbar_arrive_remote(r_a2_full);
+        if (PERSIST && blockIdx.x == 0 && threadIdx.x == 0 && ev == 5) PTRACE(A.trace, 9, 1 + half);
         if (tron) TR(trole, 4 + 2 * half);
       }
       if (!first) epi2(it - 1, prev_row, prev_slot);

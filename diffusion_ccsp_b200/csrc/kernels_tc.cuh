@@ -111,6 +111,11 @@ __device__ __forceinline__ void cluster_sync() {
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
+// src_bytes = 0: the 16 destination bytes are zero-filled and NO global read is issued (padded edge rows: thousands of them
+// would otherwise hammer the one 1 KB zero row of pe_split from every CTA — an L2 same-line hot spot)
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void *src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -738,6 +743,7 @@ struct FusedArgs {
   float *o;                  // [Epad][2][P]
   int dbg;
   long long *trace;          // harness only: clock64 timeline of CTA 0 ([role][unit < 8][16]), else nullptr
+  int pad_row_plus1;         // 1 + index of the zero row that padded edges point at (0: unknown, gather it like any row)
   // persistent mode (k_edge_fused2_tc<.., PERSIST = true>): the kernel stays resident for ALL evaluations of a sample() next to
   // the persistent node kernel and hand-shakes with it through two device counters instead of kernel boundaries
   int num_evals;             // denoiser evaluations of the sample

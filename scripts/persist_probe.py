@@ -34,3 +34,8 @@ if os.environ.get('CCSP_PERSIST_TRACE'):
         print(f'eval {i}: node signalled {tr[3][i] - base:+6d} | edge sees flag 0 | GEMM1 committed {tr[5][i] - base:+6d} | D1 ready {tr[6][i] - base:+6d} | '
               f'edge signalled {tr[7][i] - base:+6d} || node(i+1): top {tr[0][i + 1] - base:+6d} flag seen {tr[1][i + 1] - base:+6d} update {tr[2][i + 1] - base:+6d} '
               f'signalled {tr[3][i + 1] - base:+6d} | next edge flag {tr[4][i + 1] - base:+6d}  (ns)')
+    base = tr[4][5]
+    ch = [int(lib.ccsp_debug_persist_trace(8, k)) - base for k in range(16)]
+    ep = [int(lib.ccsp_debug_persist_trace(9, k)) - base for k in range(8)]
+    print('evaluation 5, CTA 0: ring stage seen full by the GEMM1 issuer, chunk 0..15 (ns after the node flag):', ch)
+    print('   epilogue thread 0: D1 in registers', ep[0], '| decoder chunk 0 / 1 published', ep[1], ep[2], '| D2 seen ready (units 0..3 mod 4)', ep[3:7])

@@ -1,4 +1,4 @@
-"""GPU: the persistent small-shard path (two kernels launched once per sample(), hand-shaking through device flags) gives
+"""GPU: the opt-in persistent small-shard path (CCSP_PERSIST=1: two kernels launched once per sample(), hand-shaking through device flags) gives
 bit-identical results to the launch-per-evaluation path — same arithmetic, same order — for Philox and injected noise, with
 history, for every pose width, and falls back by itself when the shard does not fit."""
 import os
