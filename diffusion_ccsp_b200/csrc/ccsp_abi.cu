@@ -2,6 +2,7 @@
 // the extern "C" entry points declared in include/ccsp_b200.h.
 #include "../../include/ccsp_b200.h"
 
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -162,6 +163,9 @@ struct CcspPlan {
   int device = 0;                 // the model's device, kept so that destroy works after the model is gone
   int64_t n = 0, E = 0, Epad = 0;
   int num_tiles = 0;
+  int num_chains = 1;             // independent scene groups; rows are grouped (chain, type)
+  int chain_tile0[CCSP_MAX_CHAINS + 1] = {0};   // tiles of chain c: [chain_tile0[c], chain_tile0[c + 1])
+  int chain_row0[CCSP_MAX_CHAINS + 1] = {0};    // nodes of chain c: [chain_row0[c], chain_row0[c + 1])
   DevPool pool;
   int *src_i = nullptr, *src_j = nullptr, *tile_type = nullptr, *node_ptr = nullptr, *node_src = nullptr;
   signed char *mask = nullptr;
@@ -183,7 +187,8 @@ struct CcspPlan {
   cudaStream_t capture_stream = nullptr;
   // persistent small-shard path (sample_persistent): two side streams, their events, the flag pair, device schedule arrays
   cudaStream_t ps_node = nullptr, ps_edge = nullptr;
-  cudaEvent_t pe_begin = nullptr, pe_node = nullptr, pe_edge = nullptr;
+  cudaEvent_t pe_begin = nullptr, pe_node = nullptr, pe_edge = nullptr, pe_t0 = nullptr, pe_t1 = nullptr;
+  int persist_timed_evals = 0;    // > 0: pe_t0 / pe_t1 bracket a persistent edge kernel that ran this many evaluations
   unsigned *p_flags = nullptr;
   NodeEval *p_sched = nullptr;
   int *p_eval_t = nullptr;
@@ -496,6 +501,15 @@ static void ensure_trap_word() {
   }
 }
 
+// host-mapped arrival counter of the persistent edge kernel (one increment per CTA at entry)
+static unsigned *g_arrive_host = nullptr, *g_arrive_dev = nullptr;
+static void ensure_arrival_word() {
+  if (g_arrive_host) return;
+  if (cudaHostAlloc((void **)&g_arrive_host, 64, cudaHostAllocMapped) != cudaSuccess) { g_arrive_host = nullptr; return; }
+  *g_arrive_host = 0;
+  if (cudaHostGetDevicePointer((void **)&g_arrive_dev, g_arrive_host, 0) != cudaSuccess) g_arrive_dev = nullptr;
+}
+
 // -------------------------------------------------------------------------------------------------------------------------
 // Persistent small-shard path.  When the whole sample fits on the chip at once — every edge unit on its own CTA pair plus all
 // node CTAs, counted in TPCs so that cluster placement cannot be starved: pairs + node_ctas <= num_sms / 2 — the T x (1 + K)
@@ -504,28 +518,52 @@ static void ensure_trap_word() {
 // and TMEM set-up, table loads and the W2 fetch are paid once per sample and the launch gaps disappear.  Same arithmetic in the
 // same order: results are bit-identical to the launch-per-evaluation path (tests/test_gpu_persistent.py).
 // -------------------------------------------------------------------------------------------------------------------------
-static bool persistent_eligible(const CcspPlan *p, int *pairs_out) {
+extern "C" { static int drain_timing(CcspPlan *p); }
+struct PersistCfg {
+  int pairs = 0;        // CTA pairs of the persistent edge kernel
+  int node_ctas = 0;    // CTAs of the persistent node kernel
+};
+static bool persistent_eligible(const CcspPlan *p, PersistCfg *cfg) {
   const CcspModel *m = p->m;
   const char *env = getenv("CCSP_PERSIST");
-  if (!env || env[0] == '0') return false;
-  if (m->math != CCSP_MATH_BF16X3 || p->timing_stride > 0 || p->Epad == 0) return false;
-  const int node_ctas = (int)((p->n + 1 + 63) / 64);
+  if (env && env[0] == '0') return false;
+  if (m->math != CCSP_MATH_BF16X3 || p->Epad == 0) return false;
+  const int node_blocks = (int)((p->n + 1 + 63) / 64);
   const int units = (int)(p->Epad / CCSP_TILE_M);
   const int tpcs = m->num_sms / 2;
-  const int pairs = std::min(units, tpcs - node_ctas);
-  // only while the shard is latency-bound: at most two rounds of units per pair (beyond that the launch-per-evaluation path
-  // amortises its fixed cost and uses all SMs for the edge phase)
+  if (p->num_chains > 1) {
+    // Pipelined chains (plans cut into chains at creation, CCSP_CHAINS=2..4): a few node CTAs serve all node blocks of one
+    // chain while the edge kernel, on all other SMs, works on the other chain.
+    // A tool that serialises kernels (ncu, compute-sanitizer inject through these variables) would dead-lock two
+    // co-operating kernels: stay on the launch-per-evaluation path there.
+    if (getenv("CUDA_INJECTION64_PATH") || getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") || getenv("NSIGHT_CUDA_DEBUGGER")) return false;
+    int nc = 24;
+    if (const char *e2 = getenv("CCSP_PIPE_NODE_CTAS")) nc = atoi(e2);
+    nc = std::max(2, std::min(nc, std::min(node_blocks, m->num_sms - 4)));
+    nc &= ~1;                                   // whole TPCs, so that the edge clusters keep whole TPCs too
+    int pairs = (m->num_sms - nc) / 2;
+    int umax = 0;
+    for (int c = 0; c < p->num_chains; ++c) umax = std::max(umax, p->chain_tile0[c + 1] - p->chain_tile0[c]);
+    pairs = std::min(pairs, umax);
+    if (pairs < 1) return false;
+    cfg->pairs = pairs; cfg->node_ctas = nc;
+    return true;
+  }
+  if (p->timing_stride > 0) return false;
+  const int pairs = std::min(units, tpcs - node_blocks);
+  // single chain: only while the shard is latency-bound: at most two rounds of units per pair (beyond that the
+  // launch-per-evaluation path amortises its fixed cost and uses all SMs for the edge phase)
   if (pairs < 1 || (units + pairs - 1) / pairs > 2) return false;
-  *pairs_out = pairs;
+  cfg->pairs = pairs; cfg->node_ctas = node_blocks;
   // Opt-in only (CCSP_PERSIST=1).  Measured on B200 (profiles/README.md R2.6): once padded rows stopped hammering the zero row
-  // (cp.async zero-fill), the persistent pair is no faster than two launches per evaluation on any shard size — the
-  // per-evaluation floor is the dependent chain inside the phases, not launch overhead — so the default stays with the path
-  // that needs no co-residency guarantee.
+  // (cp.async zero-fill), the single-chain persistent pair is no faster than two launches per evaluation on any shard size — the
+  // per-evaluation floor is the dependent chain inside the phases, not launch overhead.
   return env && env[0] == '1';
 }
 
 static int sample_persistent(CcspPlan *p, const CcspSchedule *s, const CcspNoise *nz, float *out, float *history, cudaStream_t user_st,
-                             int pairs) {
+                             const PersistCfg &cfg) {
+  const int pairs = cfg.pairs;
   using M = tc::Mode<tc::KIND_BF16, 3>;
   CcspModel *m = p->m;
   const int T = s->T;
@@ -561,6 +599,7 @@ static int sample_persistent(CcspPlan *p, const CcspSchedule *s, const CcspNoise
     }
   }
   const int num_evals = (int)eval_t.size();
+  if (p->persist_timed_evals > 0) { int r = drain_timing(p); if (r) return r; }
   // ---- device resources (kept on the plan) ---------------------------------------------------------------------------------
   if (!p->ps_node) {
     CCSP_CUDA_TRY(cudaStreamCreateWithFlags(&p->ps_node, cudaStreamNonBlocking));
@@ -568,7 +607,9 @@ static int sample_persistent(CcspPlan *p, const CcspSchedule *s, const CcspNoise
     CCSP_CUDA_TRY(cudaEventCreateWithFlags(&p->pe_begin, cudaEventDisableTiming));
     CCSP_CUDA_TRY(cudaEventCreateWithFlags(&p->pe_node, cudaEventDisableTiming));
     CCSP_CUDA_TRY(cudaEventCreateWithFlags(&p->pe_edge, cudaEventDisableTiming));
-    CCSP_CUDA_TRY(p->pool.alloc(&p->p_flags, 64));
+    CCSP_CUDA_TRY(cudaEventCreate(&p->pe_t0));
+    CCSP_CUDA_TRY(cudaEventCreate(&p->pe_t1));
+    CCSP_CUDA_TRY(p->pool.alloc(&p->p_flags, 64 * CCSP_MAX_CHAINS));
   }
   if (p->p_sched_cap < sched.size()) {
     CCSP_CUDA_TRY(cudaStreamSynchronize(user_st));
@@ -579,13 +620,19 @@ static int sample_persistent(CcspPlan *p, const CcspSchedule *s, const CcspNoise
   }
   CCSP_CUDA_TRY(cudaMemcpyAsync(p->p_sched, sched.data(), sched.size() * sizeof(NodeEval), cudaMemcpyHostToDevice, user_st));
   CCSP_CUDA_TRY(cudaMemcpyAsync(p->p_eval_t, eval_t.data(), eval_t.size() * sizeof(int), cudaMemcpyHostToDevice, user_st));
-  CCSP_CUDA_TRY(cudaMemsetAsync(p->p_flags, 0, 64 * sizeof(unsigned), user_st));
+  CCSP_CUDA_TRY(cudaMemsetAsync(p->p_flags, 0, 64 * CCSP_MAX_CHAINS * sizeof(unsigned), user_st));
   CCSP_CUDA_TRY(cudaEventRecord(p->pe_begin, user_st));
   CCSP_CUDA_TRY(cudaStreamWaitEvent(p->ps_edge, p->pe_begin, 0));
   CCSP_CUDA_TRY(cudaStreamWaitEvent(p->ps_node, p->pe_begin, 0));
   ensure_trap_word();
-  const unsigned node_ctas = (unsigned)((p->n + 1 + 63) / 64);
-  unsigned *node_done = p->p_flags, *edge_done = p->p_flags + 32;      // separate 128-byte lines
+  const unsigned node_ctas = (unsigned)cfg.node_ctas;
+  const int NC = p->num_chains;
+  // flag words of chain c: node_done + 32 c, edge_done + 32 c (every word on its own 128-byte line)
+  unsigned *node_done = p->p_flags, *edge_done = p->p_flags + 32 * CCSP_MAX_CHAINS;
+  // the edge clusters must all be resident before the node CTAs take SMs: they need whole TPCs, and a node CTA that got there
+  // first would leave a cluster waiting for a TPC that never frees up (both kernels run until the sample is done)
+  ensure_arrival_word();
+  if (g_arrive_host) *g_arrive_host = 0;
   // both functions are loaded before either runs (lazy module loading would otherwise stall the second launch behind the first kernel)
   CCSP_CUDA_TRY((tc::configure_node_tc_persistent<M>()));
   // ---- the edge kernel first: its clusters take whole TPCs -------------------------------------------------------------------
@@ -602,9 +649,22 @@ static int sample_persistent(CcspPlan *p, const CcspSchedule *s, const CcspNoise
   a.pad_row_plus1 = (int)p->n + 1;
     a.num_evals = num_evals; a.eval_t = p->p_eval_t; a.tb_base = m->tb; a.tb_stride = m->C * CCSP_H2;
     a.node_done = node_done; a.edge_done = edge_done; a.node_ctas = node_ctas;
+    a.num_chains = NC;
+    for (int c = 0; c <= NC; ++c) a.chain_tile0[c] = p->chain_tile0[c];
+    a.arrive = g_arrive_dev;
+    a.drain_each_eval = (NC == 1 || getenv("CCSP_PIPE_DRAIN")) ? 1 : 0;
     a.trace = getenv("CCSP_PERSIST_TRACE") ? (long long *)g_ptrace_dev : nullptr;
+    if (p->timing_stride > 0) CCSP_CUDA_TRY(cudaEventRecord(p->pe_t0, p->ps_edge));
     CCSP_CUDA_TRY((tc::launch_fused2_persistent<M>(a, pairs, p->ps_edge)));
+    if (p->timing_stride > 0) { CCSP_CUDA_TRY(cudaEventRecord(p->pe_t1, p->ps_edge)); p->persist_timed_evals = num_evals; }
     count_launch();
+  }
+  if (NC > 1 && g_arrive_host) {
+    // wait (host) until every edge CTA has started; bounded: after 20 s go on and let the flag waits' own trap decide
+    const auto t0 = std::chrono::steady_clock::now();
+    while (*(volatile unsigned *)g_arrive_host < (unsigned)(2 * pairs)) {
+      if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 20.0) break;
+    }
   }
   {
     NodeArgs a = node_args_base(p);
@@ -613,8 +673,10 @@ static int sample_persistent(CcspPlan *p, const CcspSchedule *s, const CcspNoise
     a.hist = history;
     a.sched = p->p_sched; a.num_iters = (int)sched.size(); a.nP = nP;
     a.node_done = node_done; a.edge_done = edge_done; a.edge_ctas = (unsigned)(2 * pairs);
+    a.num_chains = NC;
+    for (int c = 0; c <= NC; ++c) a.chain_row0[c] = p->chain_row0[c];
     a.trace = getenv("CCSP_PERSIST_TRACE") ? (long long *)g_ptrace_dev : nullptr;
-    CCSP_CUDA_TRY((tc::launch_node_tc_persistent<M>(a, m->blob_pose[m->math], p->ps_node)));
+    CCSP_CUDA_TRY((tc::launch_node_tc_persistent<M>(a, m->blob_pose[m->math], p->ps_node, (int)node_ctas)));
     count_launch();
   }
   CCSP_CUDA_TRY(cudaEventRecord(p->pe_edge, p->ps_edge));
@@ -707,21 +769,74 @@ int ccsp_plan_create(CcspModel *m, const float *x, int64_t n, int32_t F, const i
       ++cnt[c];
     }
   }
-  std::vector<int64_t> start(C + 1, 0);
-  std::vector<int> tile_type;
-  for (int c = 0; c < C; ++c) {
-    int64_t tiles = (cnt[c] + CCSP_PAD_M - 1) / CCSP_PAD_M * CCSP_CLUSTER;   // whole cluster groups of 128-row tiles
-    start[c + 1] = start[c] + tiles * CCSP_TILE_M;
-    for (int64_t k = 0; k < tiles; ++k) tile_type.push_back(c);
+  // ---- chains: independent groups of whole scenes (contiguous node ranges that no edge crosses) --------------------------
+  // The pipelined sampling path (sample_persistent) interleaves the chains: while the node kernel updates the nodes of one
+  // chain, the edge kernel works on another.  Rows are grouped (chain, type); within a node the accumulation order is
+  // unchanged (a node's edges all lie in its own chain, still type-major in edge order).
+  std::vector<int64_t> chain_node0 = {0, n};
+  {
+    int64_t Ev = 0;
+    for (int c = 0; c < C; ++c) Ev += cnt[c];
+    // Opt-in (CCSP_CHAINS=2..4): measured on B200 the pipelined path is no faster than two launches per evaluation at any
+    // batch size (profiles/README.md R2.8) — the SMs it takes from the edge phase for the node CTAs cost what the hidden
+    // node phase and ramps save — and every extra chain pads every type once more (+2 % rows per chain at config 2).
+    int want = 1;
+    if (const char *env = getenv("CCSP_CHAINS")) want = std::max(1, std::min(CCSP_MAX_CHAINS, atoi(env)));
+    if (want > 1 && Ev > 0) {
+      std::vector<int> cover(n + 2, 0);
+      std::vector<int64_t> below(n + 2, 0);                   // below[s] = edges with both endpoints < s
+      for (int64_t e = 0; e < E; ++e) {
+        if (etype[e] < 0) continue;
+        const int64_t i = edge_index[e], j = edge_index[E + e];
+        const int64_t lo = std::min(i, j), hi = std::max(i, j);
+        ++cover[lo + 1]; --cover[hi + 1];
+        ++below[hi + 1];
+      }
+      for (int64_t s2 = 1; s2 <= n; ++s2) { cover[s2] += cover[s2 - 1]; below[s2] += below[s2 - 1]; }
+      std::vector<int64_t> cuts;
+      int64_t prev = 0;
+      for (int k = 1; k < want; ++k) {
+        const int64_t target = Ev * k / want;
+        int64_t best = -1, best_d = -1;
+        for (int64_t s2 = prev + 1; s2 < n; ++s2) {
+          if (cover[s2] != 0) continue;                       // an edge spans the cut between nodes s2 - 1 and s2
+          const int64_t d = std::llabs(below[s2] - target);
+          if (best < 0 || d < best_d) { best = s2; best_d = d; }
+          if (below[s2] > target) break;
+        }
+        if (best < 0) break;
+        cuts.push_back(best);
+        prev = best;
+      }
+      if ((int)cuts.size() == want - 1) {
+        chain_node0.assign(1, 0);
+        for (int64_t c2 : cuts) chain_node0.push_back(c2);
+        chain_node0.push_back(n);
+      }
+    }
   }
-  const int64_t Epad = start[C];
+  const int NC = (int)chain_node0.size() - 1;
+  auto chain_of = [&](int64_t v) { int c = 0; while (c + 1 < NC && v >= chain_node0[c + 1]) ++c; return c; };
+  std::vector<int64_t> gcnt((size_t)NC * C, 0);
+  for (int64_t e = 0; e < E; ++e)
+    if (etype[e] >= 0) ++gcnt[(size_t)chain_of(edge_index[e]) * C + etype[e]];
+  std::vector<int64_t> start((size_t)NC * C + 1, 0);
+  std::vector<int> tile_type;
+  std::vector<int> chain_tile0(NC + 1, 0);
+  for (int g = 0; g < NC * C; ++g) {
+    int64_t tiles = (gcnt[g] + CCSP_PAD_M - 1) / CCSP_PAD_M * CCSP_CLUSTER;   // whole cluster groups of 128-row tiles
+    start[g + 1] = start[g] + tiles * CCSP_TILE_M;
+    for (int64_t k = 0; k < tiles; ++k) tile_type.push_back(g % C);
+    if (g % C == C - 1) chain_tile0[g / C + 1] = (int)tile_type.size();
+  }
+  const int64_t Epad = start[(size_t)NC * C];
   std::vector<int> src_i(Epad, (int)n), src_j(Epad, (int)n);   // padded rows read the zero row n
   {
-    std::vector<int64_t> fill(start.begin(), start.begin() + C);
+    std::vector<int64_t> fill(start.begin(), start.end() - 1);
     for (int64_t e = 0; e < E; ++e) {
       int c = etype[e];
       if (c < 0) continue;
-      int64_t pos = fill[c]++;
+      int64_t pos = fill[(size_t)chain_of(edge_index[e]) * C + c]++;
       src_i[pos] = (int)edge_index[e];
       src_j[pos] = (int)edge_index[E + e];
     }
@@ -756,6 +871,8 @@ int ccsp_plan_create(CcspModel *m, const float *x, int64_t n, int32_t F, const i
   CcspPlan *p = new CcspPlan();
   p->pool.cache = &m->cache;
   p->m = m; p->device = m->device; p->n = n; p->E = E; p->Epad = Epad; p->num_tiles = (int)tile_type.size();
+  p->num_chains = NC;
+  for (int c = 0; c <= NC; ++c) { p->chain_tile0[c] = chain_tile0[c]; p->chain_row0[c] = (int)chain_node0[c]; }
   auto fail = [&](int rc) { p->pool.free_all(); delete p; return rc; };
 #define PLAN_TRY(expr)                                                                             \
   do {                                                                                             \
@@ -876,6 +993,13 @@ static int drain_timing(CcspPlan *p) {
     p->timing.samples += 1; p->timing.ms_edge_l1 += a; p->timing.ms_edge_dec += b; p->timing.ms_node += c;
   }
   p->ev_used = 0;
+  if (p->persist_timed_evals > 0) {        // persistent edge kernel: its whole duration, booked as that many evaluations
+    float a = 0;
+    CCSP_CUDA_TRY(cudaEventSynchronize(p->pe_t1));
+    CCSP_CUDA_TRY(cudaEventElapsedTime(&a, p->pe_t0, p->pe_t1));
+    p->timing.samples += p->persist_timed_evals; p->timing.ms_edge_l1 += a;
+    p->persist_timed_evals = 0;
+  }
   return CCSP_OK;
 }
 
@@ -920,8 +1044,8 @@ int ccsp_sample(CcspPlan *p, const CcspSchedule *s, const CcspNoise *nz, float *
   if ((rc = ensure_time_table(m, T, st))) return rc;
   if ((rc = ensure_mode_buffers(p))) return rc;
   {
-    int pairs = 0;
-    if (persistent_eligible(p, &pairs)) return sample_persistent(p, s, nz, out, history, user_st, pairs);
+    PersistCfg cfg;
+    if (persistent_eligible(p, &cfg)) return sample_persistent(p, s, nz, out, history, user_st, cfg);
   }
 
   // sampled kernel timing: evaluation `ev_idx` is bracketed by events when selected

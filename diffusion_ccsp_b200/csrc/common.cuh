@@ -11,6 +11,7 @@
 #define CCSP_CLUSTER 2        // thread-block-cluster size of the first-layer kernel (weight-stage multicast)
 #define CCSP_PAD_M (CCSP_TILE_M * CCSP_CLUSTER)   // every constraint type is padded to whole cluster groups of tiles
 #define CCSP_MAXP 8
+#define CCSP_MAX_CHAINS 4    // independent scene groups of a plan that the pipelined sampling path interleaves
 
 namespace ccsp {
 

@@ -300,8 +300,20 @@ template <class M, bool TMA, bool PERSIST = false>
 __global__ void __launch_bounds__(Fused2Cfg<M>::THREADS, 1)
 k_edge_fused2_tc(const FusedArgs A, const __grid_constant__ PairMaps maps) {
   static_assert(!(TMA && PERSIST), "the persistent variant uses the cp.async gather");
-  const int n_ev = PERSIST ? A.num_evals : 1;
   using C = Fused2Cfg<M>;
+  // Persistent mode walks "chain evaluations" q = 0, 1, ..: evaluation q / n_ch of chain q % n_ch (FusedArgs::num_chains).
+  // Units of successive chain evaluations are dealt round-robin to the CTA pairs as ONE stream (the pair that took the last
+  // unit of q is followed by its neighbour for the first unit of q + 1), so no pair idles on a ragged last round.
+  const int n_ch = (PERSIST && A.num_chains > 1) ? A.num_chains : 1;
+  const int n_q = PERSIST ? A.num_evals * n_ch : 1;
+#define CHAIN_EVAL(q)                                                                                       \
+  const int ch = (PERSIST && n_ch > 1) ? (q) % n_ch : 0, ev = PERSIST ? (q) / n_ch : 0;                     \
+  const int tile0 = (PERSIST && n_ch > 1) ? A.chain_tile0[ch] : 0;                                          \
+  const int num_units = (PERSIST && n_ch > 1) ? A.chain_tile0[ch + 1] - tile0 : num_units_all;              \
+  int ufirst = unit0 - cbase;                                                                               \
+  if (ufirst < 0) ufirst += unit_step;                                                                      \
+  if (PERSIST) cbase = (cbase + num_units) % unit_step;                                                     \
+  (void)ev; (void)ch
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t *extra = smem + C::OFF_EXTRA;
@@ -323,7 +335,7 @@ k_edge_fused2_tc(const FusedArgs A, const __grid_constant__ PairMaps maps) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
-  const int num_units = (A.num_m_tiles / 2) * 2;             // (pair of 128-edge tiles, slot)
+  const int num_units_all = (A.num_m_tiles / 2) * 2;         // (pair of 128-edge tiles, slot)
   const int unit0 = blockIdx.x >> 1, unit_step = gridDim.x >> 1;
   const uint32_t smem_base = smem_u32(smem);
   // (Letting the peer's NON-tensor cp.async.bulk complete_tx on the leader's barrier traps on B200: its barrier has to
@@ -334,6 +346,10 @@ k_edge_fused2_tc(const FusedArgs A, const __grid_constant__ PairMaps maps) {
 
   const long long t_entry = tr ? clock64() : 0;
   if (threadIdx.x == 0) pdl_launch_dependents();
+  if (PERSIST && threadIdx.x == 0 && A.arrive) {
+    atomicAdd_system(A.arrive, 1u);
+    __threadfence_system();
+  }
   if (threadIdx.x == 0) {
     // ring 1: own gather threads + own weight loader (+ at the leader: the peer's relay lane)
     // (TMA variant: leader only, one arrive.expect_tx per loader lane of the pair: 2 x A + 2 x weights)
@@ -375,7 +391,7 @@ k_edge_fused2_tc(const FusedArgs A, const __grid_constant__ PairMaps maps) {
 #pragma unroll
         for (int s = 0; s < C::NSTAGE1; ++s) rfull[s] = mapa_u32(smem_u32(&full1[s]), 0);
         pdl_wait();                      // pe_split is written by the preceding node kernel
-        for (int u = unit0; u < num_units; u += unit_step) {
+        for (int u = unit0; u < num_units_all; u += unit_step) {
           const int m0 = ((u >> 1) * 2 + (int)rank) * SUB_M;
           int4 idx = make_int4(0, 0, 0, 0);
 #pragma unroll 1
@@ -408,16 +424,18 @@ k_edge_fused2_tc(const FusedArgs A, const __grid_constant__ PairMaps maps) {
     // in flight; the peer's barrier is forwarded to the leader by the relay lane below.
     uint32_t g = 0, it = 0;
     if (!PERSIST) pdl_wait();            // pe_split is written by the preceding node kernel
-    for (int ev = 0; ev < n_ev; ++ev) {
+    int cbase = 0;
+    for (int qe = 0; qe < n_q; ++qe) {   // (q is this thread's piece index)
+    CHAIN_EVAL(qe);
     if (PERSIST) {                       // ... or by iteration ev of the persistent node kernel (one poller per CTA)
       if (t == 0) {
-        wait_flag_ge(A.node_done, (unsigned)(ev + 1) * A.node_ctas);
-        if (blockIdx.x == 0) PTRACE(A.trace, 4, ev);
+        wait_flag_ge(A.node_done + 32 * ch, (unsigned)(ev + 1) * A.node_ctas);
+        if (blockIdx.x == 0) PTRACE(A.trace, 4, qe);
       }
       asm volatile("bar.sync 3, 128;" ::: "memory");
     }
-    for (int u = unit0; u < num_units; u += unit_step, ++it) {
-      const int m0 = ((u >> 1) * 2 + (int)rank) * SUB_M;
+    for (int u = ufirst; u < num_units; u += unit_step, ++it) {
+      const int m0 = (tile0 + (u >> 1) * 2 + (int)rank) * SUB_M;
       uint32_t roff[NP];                 // row offsets in 16-byte units (row stride 1 KB: fits 32 bits up to 4 M nodes)
       uint32_t live = 0;                 // bit p: row p of this thread is a real edge
 #pragma unroll 1
@@ -454,9 +472,11 @@ k_edge_fused2_tc(const FusedArgs A, const __grid_constant__ PairMaps maps) {
     if (lane == 0) {
       // ============ first-layer weights: this CTA's 128 of the 256 rows of every chunk =================
       uint32_t g = 0;
-      for (int ev = 0; ev < n_ev; ++ev)
-      for (int u = unit0; u < num_units; u += unit_step) {
-        const int mt = (u >> 1) * 2, slot = u & 1;
+      int cbase = 0;
+      for (int q = 0; q < n_q; ++q) {
+      CHAIN_EVAL(q);
+      for (int u = ufirst; u < num_units; u += unit_step) {
+        const int mt = tile0 + (u >> 1) * 2, slot = u & 1;
         const int grp = __ldg(&A.tile_type[mt]);
         const uint8_t *blob = A.b_blob + ((size_t)(grp * 2 + slot) * M::NKC1) * C::B1_BLOB_STAGE + rank * C::B1_PART;
         for (int kc = 0; kc < M::NKC1; ++kc, ++g) {
@@ -478,6 +498,7 @@ k_edge_fused2_tc(const FusedArgs A, const __grid_constant__ PairMaps maps) {
           if (M::NS == 2) bulk_g2s_rbar(dst + C::B1_PART, src + C::B1_BLOB_PART, C::B1_PART, bar);
         }
       }
+      }
     }
   } else if (warp == C::WARP_LOADW) {
     // (own warp: a lane that sleeps in mbarrier.try_wait holds up the other lanes of its warp)
@@ -485,8 +506,10 @@ k_edge_fused2_tc(const FusedArgs A, const __grid_constant__ PairMaps maps) {
       // ============ decoder weights: this CTA's 64 of the 128 rows, chunks in GEMM2's consumption order ==
       uint32_t g2 = 0;
       const uint8_t *blob = A.w_blob + rank * C::W_PART;
-      for (int ev = 0; ev < n_ev; ++ev)
-      for (int u = unit0; u < num_units; u += unit_step) {
+      int cbase = 0;
+      for (int qe = 0; qe < n_q; ++qe) {
+      CHAIN_EVAL(qe);
+      for (int u = ufirst; u < num_units; u += unit_step) {
         for (int q = 0; q < 8; ++q, ++g2) {
           const uint32_t s = g2 % C::NW;
           mbar_wait(&w_empty[s], ((g2 / C::NW) & 1) ^ 1);
@@ -506,6 +529,7 @@ k_edge_fused2_tc(const FusedArgs A, const __grid_constant__ PairMaps maps) {
           if (M::NS == 2) bulk_g2s_rbar(dst + C::W_PART, src + C::W_BLOB_PART, C::W_PART, bar);
         }
       }
+      }
     }
   } else if (warp == C::WARP_MMA1) {
     if (lane == 0) {
@@ -513,8 +537,10 @@ k_edge_fused2_tc(const FusedArgs A, const __grid_constant__ PairMaps maps) {
         // ============ GEMM1 issuer (M = 256 over the pair) =============================================
         uint32_t g = 0, it = 0;
         if (tr) tr[15] = t_entry;          // kernel entry of this thread (slot 15 of MMA1 / unit 0)
-        for (int ev = 0; ev < n_ev; ++ev)
-        for (int u = unit0; u < num_units; u += unit_step, ++it) {
+        int cbase = 0;
+        for (int q = 0; q < n_q; ++q) {
+        CHAIN_EVAL(q);
+        for (int u = ufirst; u < num_units; u += unit_step, ++it) {
           TR(0, 0);
           mbar_wait_cl(tempty1, (it & 1) ^ 1);
           TR(0, 1);
@@ -539,19 +565,23 @@ k_edge_fused2_tc(const FusedArgs A, const __grid_constant__ PairMaps maps) {
           if (PERSIST && blockIdx.x == 0) PTRACE(A.trace, 5, (int)it);
           TR(0, 4);
         }
+        }
       } else if (!TMA) {
         // ============ peer: forward "stage s is full here (A rows + weight half)" to the leader ==========
         uint32_t g = 0;
         uint32_t rfull[C::NSTAGE1];
 #pragma unroll
         for (int s = 0; s < C::NSTAGE1; ++s) rfull[s] = mapa_u32(smem_u32(&full1[s]), 0);
-        for (int ev = 0; ev < n_ev; ++ev)
-        for (int u = unit0; u < num_units; u += unit_step) {
+        int cbase = 0;
+        for (int q = 0; q < n_q; ++q) {
+        CHAIN_EVAL(q);
+        for (int u = ufirst; u < num_units; u += unit_step) {
           for (int kc = 0; kc < M::NKC1; ++kc, ++g) {
             const uint32_t s = g % C::NSTAGE1;
             mbar_wait(&full1[s], (g / C::NSTAGE1) & 1);
             mbar_arrive_remote(rfull[s]);
           }
+        }
         }
       }
     }
@@ -560,8 +590,10 @@ k_edge_fused2_tc(const FusedArgs A, const __grid_constant__ PairMaps maps) {
       if (leader) {
         // ============ GEMM2 issuer ======================================================================
         uint32_t g2 = 0, it = 0;
-        for (int ev = 0; ev < n_ev; ++ev)
-        for (int u = unit0; u < num_units; u += unit_step, ++it) {
+        int cbase = 0;
+        for (int qe = 0; qe < n_q; ++qe) {
+        CHAIN_EVAL(qe);
+        for (int u = ufirst; u < num_units; u += unit_step, ++it) {
           const uint32_t buf = it & 1;
           TR(1, 0);
           mbar_wait_cl(&tempty2[buf], ((it >> 1) & 1) ^ 1);
@@ -588,18 +620,22 @@ k_edge_fused2_tc(const FusedArgs A, const __grid_constant__ PairMaps maps) {
           umma_commit2(&tfull2[buf]);
           TR(1, 6);
         }
+        }
       } else if (!TMA) {
         uint32_t g2 = 0;
         uint32_t rfull[C::NW];
 #pragma unroll
         for (int s = 0; s < C::NW; ++s) rfull[s] = mapa_u32(smem_u32(&w_full[s]), 0);
-        for (int ev = 0; ev < n_ev; ++ev)
-        for (int u = unit0; u < num_units; u += unit_step) {
+        int cbase = 0;
+        for (int qe = 0; qe < n_q; ++qe) {
+        CHAIN_EVAL(qe);
+        for (int u = ufirst; u < num_units; u += unit_step) {
           for (int q = 0; q < 8; ++q, ++g2) {
             const uint32_t s = g2 % C::NW;
             mbar_wait(&w_full[s], (g2 / C::NW) & 1);
             mbar_arrive_remote(rfull[s]);
           }
+        }
         }
       }
     }
@@ -614,7 +650,7 @@ k_edge_fused2_tc(const FusedArgs A, const __grid_constant__ PairMaps maps) {
     const uint32_t r_tempty2_0 = mapa_u32(smem_u32(&tempty2[0]), 0), r_tempty2_1 = mapa_u32(smem_u32(&tempty2[1]), 0);
     const uint32_t r_a2_full = mapa_u32(smem_u32(&a2_full[cg]), 0);
     const uint64_t pol_s = l2_policy_evict_first();
-    if (threadIdx.x < 4 && unit0 < num_units && !(A.dbg & 4)) {
+    if (threadIdx.x < 4 && unit0 < num_units_all && n_ch == 1 && !(A.dbg & 4)) {
       // first unit's slice of S -> L2 while the ring fills (S is a plan constant: no need to wait for the previous kernel)
       const size_t rb = (size_t)((unit0 >> 1) * 2 + (int)rank) * 4 + threadIdx.x;
       prefetch_l2_bulk(A.S + (rb * 16 + (size_t)(unit0 & 1) * 8) * 1024, 32768, pol_s);
@@ -698,11 +734,26 @@ k_edge_fused2_tc(const FusedArgs A, const __grid_constant__ PairMaps maps) {
     size_t prev_row = 0;
     int prev_slot = 0;
     uint32_t it = 0;
-    for (int ev = 0; ev < n_ev; ++ev) {
+    int cbase = 0;
+    // Epilogue-2 is deferred by one unit.  Launch-per-evaluation mode drains it at the end of the launch; the persistent mode
+    // carries it ACROSS chain evaluations (the tensor pipe already runs the next chain's first GEMM1, and GEMM2 of the pending
+    // unit queues behind it): `o` of chain evaluation q is then complete — and edge_done signalled — after epilogue-1 of the
+    // first unit of q + 1.  It drains only when this pair has no unit in q + 1 or the sample ends.
+    bool pend = false, pend_last = false;
+    int pend_ch = 0, pend_q = 0;
+    auto signal_done = [&](int c, int qq) {   // every o row of this CTA for that chain evaluation is written: tell the node kernel
+      __threadfence();
+      asm volatile("bar.sync 2, 512;" ::: "memory");
+      if (threadIdx.x == 0) {
+        red_release_gpu_add(A.edge_done + 32 * c, 1u);
+        if (blockIdx.x == 0) PTRACE(A.trace, 7, qq);
+      }
+    };
+    for (int q = 0; q < n_q; ++q) {
+    CHAIN_EVAL(q);
     const float *tb_ev = PERSIST ? A.tb_base + (size_t)__ldg(&A.eval_t[ev]) * A.tb_stride : A.tb;
-    bool first = true;                   // epilogue-2 is deferred by one unit WITHIN an evaluation and drained at its end
-    for (int u = unit0; u < num_units; u += unit_step, ++it) {
-      const int mt = (u >> 1) * 2 + (int)rank, slot = u & 1;
+    for (int u = ufirst; u < num_units; u += unit_step, ++it) {
+      const int mt = tile0 + (u >> 1) * 2 + (int)rank, slot = u & 1;
       const int grp = __ldg(&A.tile_type[mt]);
       const size_t row = (size_t)mt * SUB_M + r;
       const int gcol0 = slot * 256 + cg * 64;
@@ -714,7 +765,7 @@ k_edge_fused2_tc(const FusedArgs A, const __grid_constant__ PairMaps maps) {
         // next unit's slice of S (4 row blocks x 32 KB contiguous) -> L2, so the register prefetch below only
         // has to cover an L2 hit
         const int un = u + unit_step;
-        const size_t rb = (size_t)((un >> 1) * 2 + (int)rank) * 4 + threadIdx.x;
+        const size_t rb = (size_t)(tile0 + (un >> 1) * 2 + (int)rank) * 4 + threadIdx.x;
         prefetch_l2_bulk(A.S + (rb * 16 + (size_t)(un & 1) * 8) * 1024, 32768, pol_s);
       }
       float *tbu = tb_s + (it & 1) * 256;
@@ -726,7 +777,7 @@ k_edge_fused2_tc(const FusedArgs A, const __grid_constant__ PairMaps maps) {
       if (tron) TR(trole, 1);
       // ---- epilogue-1: D1 -> decoder operand chunks -------------------------------------------------
       mbar_wait_cl(tfull1, it & 1);
-      if (PERSIST && blockIdx.x == 0 && threadIdx.x == 0) PTRACE(A.trace, 6, ev);
+      if (PERSIST && blockIdx.x == 0 && threadIdx.x == 0) PTRACE(A.trace, 6, q);
       if (tron) TR(trole, 2);
       tc_fence_after();
       const uint32_t taddr1 = tmem_base + cg * 64 + ((uint32_t)(quarter * 32) << 16);
@@ -771,23 +822,32 @@ k_edge_fused2_tc(const FusedArgs A, const __grid_constant__ PairMaps maps) {
         if (PERSIST && blockIdx.x == 0 && threadIdx.x == 0 && ev == 5) PTRACE(A.trace, 9, 1 + half);
         if (tron) TR(trole, 4 + 2 * half);
       }
-      if (!first) epi2(it - 1, prev_row, prev_slot);
-      first = false;
+      if (pend) {
+        epi2(it - 1, prev_row, prev_slot);
+        if (PERSIST && pend_last) signal_done(pend_ch, pend_q);
+      }
+      pend = true; pend_last = u + unit_step >= num_units; pend_ch = ch; pend_q = q;
       prev_row = row; prev_slot = slot;
     }
-    if (!first) epi2(it - 1, prev_row, prev_slot);
-    if (PERSIST) {                       // every o row of this CTA for evaluation ev is written: tell the node kernel
-      __threadfence();
-      asm volatile("bar.sync 2, 512;" ::: "memory");
-      if (threadIdx.x == 0) {
-        red_release_gpu_add(A.edge_done, 1u);
-        if (blockIdx.x == 0) PTRACE(A.trace, 7, ev);
-      }
+    if (PERSIST && ufirst >= num_units) signal_done(ch, q);     // no unit of this chain evaluation here: nothing to wait for
+    bool drain = pend;
+    if (PERSIST && pend && q + 1 < n_q) {                       // keep it pending if a unit of q + 1 follows on this pair
+      const int cn = n_ch > 1 ? (q + 1) % n_ch : 0;
+      const int units_n = n_ch > 1 ? A.chain_tile0[cn + 1] - A.chain_tile0[cn] : num_units_all;
+      int uf = unit0 - cbase;
+      if (uf < 0) uf += unit_step;
+      drain = uf >= units_n || A.drain_each_eval;
+    }
+    if (drain) {
+      epi2(it - 1, prev_row, prev_slot);
+      if (PERSIST) signal_done(pend_ch, pend_q);
+      pend = false;
     }
     }
   }
 #undef TR
 #undef TRP
+#undef CHAIN_EVAL
 #undef REG_DEC
 #undef REG_INC
   tc_fence_before();

@@ -69,7 +69,6 @@ __global__ void __launch_bounds__(NodeTcCfg<M>::THREADS, 1) k_node_tc(const Node
   constexpr int EW = C::EW;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int row0 = blockIdx.x * C::ROWS;
   const int P = PT ? PT : A0.P;
   const uint32_t smem_base = smem_u32(smem);
   long long *const tr = (!PERSIST && A0.trace && blockIdx.x == 1 && (tid == 0 || tid == C::ROW_THREADS)) ? A0.trace + (tid == 0 ? 0 : 16) : nullptr;
@@ -97,12 +96,23 @@ __global__ void __launch_bounds__(NodeTcCfg<M>::THREADS, 1) k_node_tc(const Node
     if (tid < CCSP_H) b2s[tid] = __ldg(&A0.b2[tid]);
   }
   const int r = tid & (C::ROWS - 1), part = tid >> 6;         // row threads: node row, 1 of 8 helpers of that row
-  const int v = row0 + r;
   const int n_iters = PERSIST ? A0.num_iters : 1;
+  // persistent mode: every iteration visits the plan's chains in turn (NodeArgs::num_chains), and within a chain this CTA
+  // takes the 64-row blocks blockIdx.x, + gridDim.x, ..  (launch-per-iteration mode: one chain, one block per CTA)
+  const int n_ch = (PERSIST && A0.num_chains > 1) ? A0.num_chains : 1;
+  uint32_t nblk_done = 0;                // blocks this CTA has pushed through the tensor core (phase of tfull)
 #pragma unroll 1
   for (int iter = 0; iter < n_iters; ++iter) {
+#pragma unroll 1
+  for (int ch = 0; ch < n_ch; ++ch) {
   NodeArgs A = A0;                       // this iteration's arguments
-  PTRACE(ptr_, 0, iter);
+  const int crow0 = n_ch > 1 ? A0.chain_row0[ch] : 0;                     // rows of this chain: [crow0, cend)
+  const int cend = n_ch > 1 ? A0.chain_row0[ch + 1] : A0.n;
+  const int ccopy_end = n_ch > 1 ? cend : A0.n + 1;    // (+ the zero row n; the persistent edge kernel zero-fills padded rows itself)
+  const int nblk = (ccopy_end - crow0 + C::ROWS - 1) / C::ROWS;
+  bool need_wait = PERSIST && iter > 0;  // the edge kernel's evaluation iter - 1 of this chain has to be complete
+  const int tq = iter * n_ch + ch;       // trace slot
+  PTRACE(ptr_, 0, tq);
   if (PERSIST) {
     const NodeEval E = A0.sched[iter];
     A.mode = E.mode; A.pin = E.pin; A.a = E.a; A.b = E.b; A.c1 = E.c1; A.c2 = E.c2; A.sigma = E.sigma;
@@ -110,8 +120,12 @@ __global__ void __launch_bounds__(NodeTcCfg<M>::THREADS, 1) k_node_tc(const Node
     A.z = A0.z ? A0.z + (size_t)E.draw * A0.nP : nullptr;
     A.hist = (A0.hist && E.hist_slot >= 0) ? A0.hist + (size_t)E.hist_slot * A0.nP : nullptr;
   }
+#pragma unroll 1
+  for (int blk = blockIdx.x; blk < nblk; blk += PERSIST ? (int)gridDim.x : nblk) {
+  const int row0 = crow0 + blk * C::ROWS;
+  const int v = row0 + r;
   if (tid < C::ROW_THREADS) {
-    if (part == 1 && v < A.n && !A.z &&
+    if (part == 1 && v < cend && !A.z &&
         (A.mode == NODE_DDPM || A.mode == NODE_ULA || (A.mode == NODE_INIT && !A.has_xinit))) {
       float zz[CCSP_MAXP];               // the node's Philox draw, computed off the summing thread's critical path
 #pragma unroll
@@ -124,7 +138,7 @@ __global__ void __launch_bounds__(NodeTcCfg<M>::THREADS, 1) k_node_tc(const Node
   // Everything below this line and above pdl_wait() reads only plan constants (graph structure, mask, pinned poses,
   // injected noise), so it runs under the tail of the preceding edge kernel: after the wait one dependent load level
   // (the decoder outputs o, and x) is left on the critical path instead of three.
-  const bool reduce = tid < C::ROW_THREADS && v < A.n && A.mode != NODE_INIT && A.mode != NODE_ENCODE;
+  const bool reduce = tid < C::ROW_THREADS && v < cend && A.mode != NODE_INIT && A.mode != NODE_ENCODE;
   int k0 = 0, k1 = 0;
   bool masked = false;
   float x_old[CCSP_MAXP], z_in[CCSP_MAXP], aux[CCSP_MAXP], gtv[CCSP_MAXP];   // state of the node's summing thread (part == 0)
@@ -132,7 +146,7 @@ __global__ void __launch_bounds__(NodeTcCfg<M>::THREADS, 1) k_node_tc(const Node
   for (int p = 0; p < CCSP_MAXP; ++p) { x_old[p] = 0.f; z_in[p] = 0.f; aux[p] = 0.f; gtv[p] = 0.f; }
   int src[4] = {0, 0, 0, 0};
   int cnt = 0;
-  if (tid < C::ROW_THREADS && v < A.n && A.mode != NODE_ENCODE) {
+  if (tid < C::ROW_THREADS && v < cend && A.mode != NODE_ENCODE) {
     masked = A.mask[v] != 0;
     if (tid < C::ROWS) {
       const size_t ix = (size_t)v * P;
@@ -156,15 +170,16 @@ __global__ void __launch_bounds__(NodeTcCfg<M>::THREADS, 1) k_node_tc(const Node
   }
   if (!PERSIST) {
     pdl_wait();                          // o / x / pe are produced (or still read) by the preceding edge kernel
-  } else if (iter > 0) {                 // ... or by evaluation iter - 1 of the persistent edge kernel
-    if (tid == 0) wait_flag_ge(A0.edge_done, (unsigned)iter * A0.edge_ctas);
+  } else if (need_wait) {                // ... or by evaluation iter - 1 of the persistent edge kernel
+    if (tid == 0) wait_flag_ge(A0.edge_done + 32 * ch, (unsigned)iter * A0.edge_ctas);
     __syncthreads();
-    PTRACE(ptr_, 1, iter);
+    need_wait = false;
+    PTRACE(ptr_, 1, tq);
   }
 
   // ---- phase 1a: the 8 threads of a node fetch its incident decoder outputs in parallel -------------------------
   if (tid < C::ROW_THREADS) {
-    if (tid < C::ROWS && v < A.n && A.mode != NODE_ENCODE && A.mode != NODE_INIT) {
+    if (tid < C::ROWS && v < cend && A.mode != NODE_ENCODE && A.mode != NODE_INIT) {
       const size_t ix = (size_t)v * P;
 #pragma unroll
       for (int p = 0; p < CCSP_MAXP; ++p)
@@ -200,7 +215,7 @@ __global__ void __launch_bounds__(NodeTcCfg<M>::THREADS, 1) k_node_tc(const Node
     float xn[CCSP_MAXP];
 #pragma unroll
     for (int p = 0; p < CCSP_MAXP; ++p) xn[p] = 0.f;
-    if (v < A.n) {
+    if (v < cend) {
       const size_t ix = (size_t)v * P;
       if (A.mode == NODE_ENCODE) {
         _Pragma("unroll") for (int p = 0; p < CCSP_MAXP; ++p) if (p < P) xn[p] = A.x_in[ix + p];
@@ -289,7 +304,7 @@ __global__ void __launch_bounds__(NodeTcCfg<M>::THREADS, 1) k_node_tc(const Node
     for (int p = 0; p < CCSP_MAXP; ++p) xs[r][p] = xn[p];
   }
   NTR(3);
-  PTRACE(ptr_, 2, iter);
+  PTRACE(ptr_, 2, tq);
   __syncthreads();                       // xs; the scratch (= A operand region) is free again
   NTR(4);
 
@@ -342,7 +357,7 @@ __global__ void __launch_bounds__(NodeTcCfg<M>::THREADS, 1) k_node_tc(const Node
     // ---- phase 3: warp w <-> TMEM lanes 32 (w & 3).. (only lanes 0..63 hold nodes), columns 64 (w >> 2).. +63 ----
     const int quarter = warp & 3, cg = warp >> 2;
     const int rr = quarter * 32 + lane, vv = row0 + rr;
-    mbar_wait(tfull, iter & 1);
+    mbar_wait(tfull, nblk_done & 1);
     NTR(7);
     tc_fence_after();
     const uint32_t taddr = tmem_base + cg * 64 + ((uint32_t)(quarter * 32) << 16);
@@ -380,7 +395,7 @@ __global__ void __launch_bounds__(NodeTcCfg<M>::THREADS, 1) k_node_tc(const Node
 #pragma unroll 1
     for (int i = 0; i < C::ROWS / 16; ++i) {
       const int rr = warp * (C::ROWS / 16) + i, vv = row0 + rr;
-      if (vv > A.n) break;
+      if (vv >= ccopy_end) break;
       const uint8_t *src = smem + (size_t)rr * M::PE_ROW_BYTES;
       uint8_t *dst = reinterpret_cast<uint8_t *>(A.pe) + (size_t)vv * M::PE_ROW_BYTES;
       // global 16-byte slot g of the row holds piece (g & 3) of part ((g >> 2) & 1) of k-chunk (g >> 3)  (Mode::pe_off);
@@ -394,11 +409,19 @@ __global__ void __launch_bounds__(NodeTcCfg<M>::THREADS, 1) k_node_tc(const Node
     }
   }
   NTR(10);
-  if (PERSIST) {                         // x / history / pe of this iteration are written: tell the edge kernel; the staging rows
-    __threadfence();                     // (= next iteration's scratch) are free after the barrier
+  ++nblk_done;
+  if (PERSIST) __syncthreads();          // the staging rows (= the next block's scratch) are free again
+  }
+  if (PERSIST) {                         // x / history / pe of this chain and iteration are written: tell the edge kernel
+    if (need_wait) {                     // (a CTA without blocks in this chain still keeps step with the edge kernel)
+      if (tid == 0) wait_flag_ge(A0.edge_done + 32 * ch, (unsigned)iter * A0.edge_ctas);
+      __syncthreads();
+    }
+    __threadfence();
     __syncthreads();
-    if (tid == 0) red_release_gpu_add(A0.node_done, 1u);
-    PTRACE(ptr_, 3, iter);
+    if (tid == 0) red_release_gpu_add(A0.node_done + 32 * ch, 1u);
+    PTRACE(ptr_, 3, tq);
+  }
   }
   }
   if (warp == C::ROW_THREADS / 32) tmem_dealloc(*tmem_ptr, 256);
@@ -448,12 +471,12 @@ cudaError_t configure_node_tc_persistent() {
   return cudaSuccess;
 }
 template <class M>
-cudaError_t launch_node_tc_persistent(const NodeArgs &a, const uint8_t *w2_blob, cudaStream_t st) {
+cudaError_t launch_node_tc_persistent(const NodeArgs &a, const uint8_t *w2_blob, cudaStream_t st, int ctas = 0) {
   using C = NodeTcCfg<M>;
   cudaError_t e0 = configure_node_tc_persistent<M>();
   if (e0 != cudaSuccess) return e0;
   if (a.num_iters <= 0 || !a.sched) return cudaErrorInvalidValue;
-  const unsigned blocks = (unsigned)((a.n + 1 + C::ROWS - 1) / C::ROWS);
+  const unsigned blocks = ctas > 0 ? (unsigned)ctas : (unsigned)((a.n + 1 + C::ROWS - 1) / C::ROWS);
   k_node_tc<M, 0, true><<<blocks, C::THREADS, C::SMEM_BYTES, st>>>(a, w2_blob);
   return cudaGetLastError();
 }

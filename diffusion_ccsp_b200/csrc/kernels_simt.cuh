@@ -162,6 +162,11 @@ struct NodeArgs {
   unsigned *node_done;           // += 1 per CTA and iteration (x and pe of the iteration are written)
   unsigned *edge_done;           // iteration i >= 1 may start once it reaches i * edge_ctas
   unsigned edge_ctas;
+  // pipelined chains (persistent mode): chain c owns node rows chain_row0[c] .. chain_row0[c + 1] (whole scenes) and the flag
+  // words node_done + 32 c / edge_done + 32 c; a CTA walks the 64-row blocks blockIdx.x, + gridDim.x, .. of every chain in
+  // turn, so a few node CTAs serve all nodes while the edge kernel works on the other chain.  num_chains <= 1: all rows.
+  int num_chains;
+  int chain_row0[CCSP_MAX_CHAINS + 1];
 };
 
 // per-iteration arguments of the persistent node kernel (what ccsp_sample passes per launch otherwise)

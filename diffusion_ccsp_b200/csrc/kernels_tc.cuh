@@ -753,6 +753,14 @@ struct FusedArgs {
   unsigned *node_done;       // += 1 per node CTA and node iteration; evaluation ev may gather once it reaches (ev + 1) * node_ctas
   unsigned *edge_done;       // += 1 per edge CTA and evaluation (all of its o rows written)
   unsigned node_ctas;
+  // pipelined chains (persistent mode only): the plan's tiles are grouped into num_chains independent scene groups ("chains");
+  // chain c owns tiles chain_tile0[c] .. chain_tile0[c + 1] and the flag words node_done + 32 c / edge_done + 32 c.  The
+  // kernel runs (evaluation 0, chain 0), (0, 1), .., (1, 0), ..: while the node kernel updates the nodes of one chain, the
+  // tensor pipe works on another chain, and the operand pipeline never drains.  num_chains <= 1: one chain = all tiles.
+  int num_chains;
+  int chain_tile0[CCSP_MAX_CHAINS + 1];
+  int drain_each_eval;       // 1: epilogue-2 is drained at the end of every chain evaluation (0: carried into the next one)
+  unsigned *arrive;          // host-mapped counter, += 1 per CTA at entry (the host launches the node kernel once all are resident)
 };
 
 // ---- device-scope flags of the persistent pair of kernels ------------------------------------------------------------

@@ -76,3 +76,59 @@ def test_large_shards_fall_back_to_the_launch_per_evaluation_path():
     out, launches = run(batch, 'qualitative', False, 2, 2, persist=True, trained=True, seed=5)
     assert launches - (1 + 2 * 2 * 3) in (0, 2)                       # 645 units do not fit next to 145 node CTAs
     assert bool(torch.isfinite(out).all())
+
+
+# ---- pipelined chains (opt-in, CCSP_CHAINS=2..4 at plan creation): the plan is cut into independent scene groups, the persistent
+# edge kernel walks (evaluation, chain) pairs while a few persistent node CTAs serve the node blocks of the other chain -------------
+def run_chains(batch, mode, tri, T, K, chains, node_ctas=None, EBM='ULA', trained=False, **kw):
+    dims = synthetic.dims_for(mode, tri)
+    sd = synthetic.load_trained_checkpoint() if trained else synthetic.make_state_dict(dims, mode, seed=3)
+    den = ConstraintDiffuser(dims=dims, input_mode=mode, device='cuda', verbose=False, math='bf16x3')
+    gd = GaussianDiffusion(den, timesteps=T, EBM=EBM, samples_per_step=K if K else 10).eval()
+    gd.load_state_dict(sd, strict=False)
+    os.environ['CCSP_CHAINS'] = str(chains)
+    if node_ctas:
+        os.environ['CCSP_PIPE_NODE_CTAS'] = str(node_ctas)
+    try:
+        den.plan_for(batch)
+        _abi.reset_launch_count()
+        out = gd.sample(batch, **kw)
+        torch.cuda.synchronize()
+        return out, _abi.launch_count()
+    finally:
+        os.environ.pop('CCSP_CHAINS', None)
+        os.environ.pop('CCSP_PIPE_NODE_CTAS', None)
+
+
+@pytest.mark.parametrize('chains,node_ctas', [(2, 8), (3, 24), (4, 2)])
+def test_pipelined_chains_equal_launch_per_evaluation(chains, node_ctas):
+    batch = scenes.qualitative_batch(200, 8)                  # 1800 nodes, ~15.8 k edges: several units per pair and chain
+    T, K = 8, 4
+    a, la = run_chains(batch, 'qualitative', False, T, K, 1, trained=True, seed=21)
+    b, lb = run_chains(batch, 'qualitative', False, T, K, chains, node_ctas, trained=True, seed=21)
+    assert la - (1 + 2 * T * (1 + K)) in (0, 2) and lb in (2, 4), (la, lb)      # two launches per sample
+    assert same_bits(a, b)
+    c, _ = run_chains(batch, 'qualitative', False, T, K, chains, node_ctas, trained=True, seed=22)
+    assert not same_bits(b, c)
+
+
+def test_pipelined_chains_history_noise_and_other_worlds():
+    batch = scenes.qualitative_batch(48, 4)
+    T, K = 5, 3
+    noise = torch.from_numpy(np.random.default_rng(1).standard_normal((1 + T * (1 + K), batch.num_nodes, 4), dtype=np.float32))
+    (a, ha), _ = run_chains(batch, 'qualitative', False, T, K, 1, trained=True, noise=noise, return_history=True)
+    (b, hb), lb = run_chains(batch, 'qualitative', False, T, K, 2, 4, trained=True, noise=noise, return_history=True)
+    assert lb in (2, 4) and same_bits(a, b) and all(same_bits(x, y) for x, y in zip(ha, hb))
+    for mode, tri, factory in (('diffuse_pairwise', False, lambda: scenes.make_batch('boxes', 64, 12, seed=1)),
+                               ('robot_box', False, lambda: scenes.make_batch('robot_box', 96, 6, seed=3))):
+        bt = factory()
+        a, _ = run_chains(bt, mode, tri, 6, 3, 1, seed=5)
+        b, lb = run_chains(bt, mode, tri, 6, 3, 3, 6, seed=5)
+        assert lb in (2, 4) and same_bits(a, b)
+
+
+def test_chain_cut_needs_independent_scene_groups():
+    """one scene cannot be cut: the plan stays a single chain and sampling takes the default path"""
+    batch = scenes.qualitative_batch(1, 4)
+    out, launches = run_chains(batch, 'qualitative', False, 3, 2, 2, trained=True, seed=1)
+    assert launches - (1 + 2 * 3 * 3) in (0, 2) and bool(torch.isfinite(out).all())
