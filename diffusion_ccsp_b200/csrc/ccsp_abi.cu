@@ -958,6 +958,8 @@ void ccsp_plan_destroy(CcspPlan *p) {
   if (p->pe_begin) cudaEventDestroy(p->pe_begin);
   if (p->pe_node) cudaEventDestroy(p->pe_node);
   if (p->pe_edge) cudaEventDestroy(p->pe_edge);
+  if (p->pe_t0) cudaEventDestroy(p->pe_t0);
+  if (p->pe_t1) cudaEventDestroy(p->pe_t1);
   p->pool.free_all();
   delete p;
   cudaSetDevice(prev);

@@ -231,11 +231,21 @@ __device__ __forceinline__ void issue_chunk2(uint32_t d_tmem, uint32_t a_hi, uin
 }
 
 // one k-step (K = 16) of the same
-template <class M, int NTILE>
+// A128: the A stage holds rows of 128 B, [hi 64 B | lo 64 B] of the k-chunk, in SWIZZLE_128B (the gathered first-layer operand:
+// a gathered row lands as ONE 128-byte shared-memory line instead of two 64-byte halves in separate hi / lo tiles)
+template <class M, int NTILE, bool A128 = false>
 __device__ __forceinline__ void issue_kstep2(uint32_t d_tmem, uint32_t a_hi, uint32_t b_hi, uint32_t b_part, int ks, bool zero) {
   constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NTILE >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
   const uint32_t ko = ks * 32;
-  const uint32_t a_lo = a_hi + PART, b_lo = b_hi + b_part;
+  const uint32_t b_lo = b_hi + b_part;
+  if (A128) {
+    static_assert(!A128 || M::NSPLIT == 3, "the 128-byte A rows hold a hi and a lo slice");
+    umma2_f16(d_tmem, smem_desc_sw128(a_hi + ROWB + ko), smem_desc_sw64(b_hi + ko), idesc, !zero);
+    umma2_f16(d_tmem, smem_desc_sw128(a_hi + ko), smem_desc_sw64(b_lo + ko), idesc, 1);
+    umma2_f16(d_tmem, smem_desc_sw128(a_hi + ko), smem_desc_sw64(b_hi + ko), idesc, 1);
+    return;
+  }
+  const uint32_t a_lo = a_hi + PART;
   if (M::NSPLIT == 3) {
     umma2_f16(d_tmem, smem_desc_sw64(a_lo + ko), smem_desc_sw64(b_hi + ko), idesc, !zero);
     umma2_f16(d_tmem, smem_desc_sw64(a_hi + ko), smem_desc_sw64(b_lo + ko), idesc, 1);
@@ -263,6 +273,8 @@ template <class M>
 struct Fused2Cfg {
   static_assert(M::KIND == KIND_BF16, "one 32-column epilogue chunk = one BF16 k-chunk of the decoder");
   static constexpr int NT1 = 256, NT2 = 128;
+  // cp.async gather variant with split operands: A rows of ring 1 are 128 B ([hi | lo]) in SWIZZLE_128B (see issue_kstep2)
+  static constexpr bool A128 = M::NS == 2;
   static constexpr int B1_PART = (NT1 / 2) * ROWB;            // this CTA's 128 weight rows of one operand part: 8 KB
   static constexpr int B1_STAGE = M::NS * B1_PART;
   static constexpr int B1_BLOB_PART = NT1 * ROWB;             // part size in the packed blob (256 rows)
@@ -455,10 +467,11 @@ k_edge_fused2_tc(const FusedArgs A, const __grid_constant__ PairMaps maps) {
         if (t == 0) TR(6, kc);
         if (!(A.dbg & 1)) {
           const uint32_t koff = M::pe_off(kc % (M::NKC1 / 2), part, q);
-          const uint32_t st = smem_base + s * C::STAGE1 + part * PART;
+          const uint32_t st = smem_base + s * C::STAGE1 + (C::A128 ? 0 : part * PART);
 #pragma unroll
           for (int p = 0; p < NP; ++p)
-            cp_async16_zfill(st + sw64_off(r0 + RPP * p, q), A.pe_split + (size_t)roff[p] * 16 + koff, ((live >> p) & 1u) ? 16u : 0u);
+            cp_async16_zfill(st + (C::A128 ? sw128_off(r0 + RPP * p, q8) : sw64_off(r0 + RPP * p, q)),
+                             A.pe_split + (size_t)roff[p] * 16 + koff, ((live >> p) & 1u) ? 16u : 0u);
         }
         cp_async_arrive_noinc(&full1[s]);
         if (t == 0) TR(7, kc);
@@ -554,11 +567,11 @@ k_edge_fused2_tc(const FusedArgs A, const __grid_constant__ PairMaps maps) {
             if (kc == 8) TR(0, 3);
             tc_fence_after();
             const uint32_t a_hi = smem_base + s * C::STAGE1;
-            if (!(A.dbg & 8)) issue_kstep2<M, C::NT1>(tmem_base, a_hi, a_hi + M::A_STAGE, C::B1_PART, 0, kc == 0);
+            if (!(A.dbg & 8)) issue_kstep2<M, C::NT1, C::A128 && !TMA>(tmem_base, a_hi, a_hi + M::A_STAGE, C::B1_PART, 0, kc == 0);
             // peek at the next stage while this chunk's MMAs are queued, so that its first MMA can follow the commit
             // without the barrier round trip (non-blocking: a blocking wait here would delay this stage's release)
             ready = kc + 1 < M::NKC1 && mbar_test_wait(&full1[(g + 1) % C::NSTAGE1], ((g + 1) / C::NSTAGE1) & 1);
-            if (!(A.dbg & 8)) issue_kstep2<M, C::NT1>(tmem_base, a_hi, a_hi + M::A_STAGE, C::B1_PART, 1, false);
+            if (!(A.dbg & 8)) issue_kstep2<M, C::NT1, C::A128 && !TMA>(tmem_base, a_hi, a_hi + M::A_STAGE, C::B1_PART, 1, false);
             umma_commit2(&empty1[s]);
           }
           umma_commit2(tfull1);

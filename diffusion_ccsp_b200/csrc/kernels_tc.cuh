@@ -182,6 +182,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
 __device__ __forceinline__ uint64_t smem_desc_sw64(uint32_t saddr) {
   return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (4ull << 61);
 }
+// SWIZZLE_128B K-major tile (rows of 128 B, 8-row groups of 1024 B): layout type 2, SBO = 1024 B.  The start address may be
+// advanced by multiples of 32 B inside the 128-byte row (one K = 16 BF16 step each): the XOR acts on absolute address bits.
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// byte offset of 16-byte piece `q` (0..7) of row `r` inside a SWIZZLE_128B operand tile (Swizzle<3,4,3>)
+__host__ __device__ __forceinline__ uint32_t sw128_off(uint32_t r, uint32_t q) { return r * 128 + ((q ^ (r & 7)) << 4); }
 // byte offset of 16-byte piece `q` (0..3) of row `r` inside a SWIZZLE_64B operand tile (Swizzle<2,4,3>)
 __host__ __device__ __forceinline__ uint32_t sw64_off(uint32_t r, uint32_t q) { return r * ROWB + ((q ^ ((r >> 1) & 3)) << 4); }
 

@@ -1,8 +1,9 @@
 #!/bin/bash
 set -u
-O=gpurun_out/r2x; mkdir -p $O
-timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_persistent.py -x -q 2>&1 | tail -5
-for nc in 2 3; do
-echo "== config 2, T=150, chains $nc"; PROBE_CHAINS=$nc timeout 300 python scripts/pipe_probe.py 1024 8 150 10 20 24 2>&1 | tee $O/probe_cfg2_c$nc.txt | tail -4
-echo "== config 2, T=150, chains $nc, drain"; CCSP_PIPE_DRAIN=1 PROBE_CHAINS=$nc timeout 300 python scripts/pipe_probe.py 1024 8 150 10 24 2>&1 | tail -1
-done
+O=gpurun_out/r2z; mkdir -p $O
+timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -k "bf16" 2>&1 | tail -4
+timeout 600 python bench.py --steps 3 --warmup 2 --no-cpu-baseline --no-e2e 2>$O/bench.err | tee $O/bench.json | python -c "
+import sys, json
+d = json.loads(sys.stdin.read().strip().splitlines()[-1])
+print({k: d[k] for k in ('value', 'ms_per_step', 'clocks')}, d['roofline']['avg_launch_ms'], d['roofline']['frac'], d['kernels']['avg_ms'])"
+tail -2 $O/bench.err
