@@ -522,6 +522,7 @@ extern "C" { static int drain_timing(CcspPlan *p); }
 struct PersistCfg {
   int pairs = 0;        // CTA pairs of the persistent edge kernel
   int node_ctas = 0;    // CTAs of the persistent node kernel
+  int partition = 0;    // chains: 1 = every node CTA serves one chain, one block each (small shards)
 };
 static bool persistent_eligible(const CcspPlan *p, PersistCfg *cfg) {
   const CcspModel *m = p->m;
@@ -537,14 +538,20 @@ static bool persistent_eligible(const CcspPlan *p, PersistCfg *cfg) {
     // A tool that serialises kernels (ncu, compute-sanitizer inject through these variables) would dead-lock two
     // co-operating kernels: stay on the launch-per-evaluation path there.
     if (getenv("CUDA_INJECTION64_PATH") || getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") || getenv("NSIGHT_CUDA_DEBUGGER")) return false;
+    int bmax = 0;
+    for (int c = 0; c < p->num_chains; ++c) bmax = std::max(bmax, (p->chain_row0[c + 1] - p->chain_row0[c] + 63) / 64);
     int nc = 24;
-    if (const char *e2 = getenv("CCSP_PIPE_NODE_CTAS")) nc = atoi(e2);
-    nc = std::max(2, std::min(nc, std::min(node_blocks, m->num_sms - 4)));
-    nc &= ~1;                                   // whole TPCs, so that the edge clusters keep whole TPCs too
+    if (bmax * p->num_chains <= 48 && !getenv("CCSP_PIPE_NODE_CTAS")) {
+      // small shard: SMs are plentiful, so every chain gets its own node CTAs, one 64-node block each
+      nc = bmax * p->num_chains;
+      cfg->partition = 1;
+    } else {
+      if (const char *e2 = getenv("CCSP_PIPE_NODE_CTAS")) nc = atoi(e2);
+      nc = std::max(2, std::min(nc, std::min(node_blocks, m->num_sms - 4)));
+    }
+    nc = (nc + 1) & ~1;                         // whole TPCs, so that the edge clusters keep whole TPCs too
     int pairs = (m->num_sms - nc) / 2;
-    int umax = 0;
-    for (int c = 0; c < p->num_chains; ++c) umax = std::max(umax, p->chain_tile0[c + 1] - p->chain_tile0[c]);
-    pairs = std::min(pairs, umax);
+    pairs = std::min(pairs, units);
     if (pairs < 1) return false;
     cfg->pairs = pairs; cfg->node_ctas = nc;
     return true;
@@ -652,7 +659,9 @@ static int sample_persistent(CcspPlan *p, const CcspSchedule *s, const CcspNoise
     a.num_chains = NC;
     for (int c = 0; c <= NC; ++c) a.chain_tile0[c] = p->chain_tile0[c];
     a.arrive = g_arrive_dev;
-    a.drain_each_eval = (NC == 1 || getenv("CCSP_PIPE_DRAIN")) ? 1 : 0;
+    for (int c = 0; c < NC; ++c) a.chain_nblk[c] = (unsigned)((p->chain_row0[c + 1] - p->chain_row0[c] + 63) / 64);
+    // carry epilogue-2 across chain evaluations only where a pair has several units per chain evaluation to hide it behind
+    a.drain_each_eval = (NC == 1 || cfg.partition || getenv("CCSP_PIPE_DRAIN")) ? 1 : 0;
     a.trace = getenv("CCSP_PERSIST_TRACE") ? (long long *)g_ptrace_dev : nullptr;
     if (p->timing_stride > 0) CCSP_CUDA_TRY(cudaEventRecord(p->pe_t0, p->ps_edge));
     CCSP_CUDA_TRY((tc::launch_fused2_persistent<M>(a, pairs, p->ps_edge)));
@@ -675,6 +684,8 @@ static int sample_persistent(CcspPlan *p, const CcspSchedule *s, const CcspNoise
     a.node_done = node_done; a.edge_done = edge_done; a.edge_ctas = (unsigned)(2 * pairs);
     a.num_chains = NC;
     for (int c = 0; c <= NC; ++c) a.chain_row0[c] = p->chain_row0[c];
+    for (int c = 0; c < NC; ++c) a.chain_units[c] = (unsigned)(p->chain_tile0[c + 1] - p->chain_tile0[c]);
+    a.node_partition = cfg.partition;
     a.trace = getenv("CCSP_PERSIST_TRACE") ? (long long *)g_ptrace_dev : nullptr;
     CCSP_CUDA_TRY((tc::launch_node_tc_persistent<M>(a, m->blob_pose[m->math], p->ps_node, (int)node_ctas)));
     count_launch();

@@ -440,11 +440,13 @@ k_edge_fused2_tc(const FusedArgs A, const __grid_constant__ PairMaps maps) {
     for (int qe = 0; qe < n_q; ++qe) {   // (q is this thread's piece index)
     CHAIN_EVAL(qe);
     if (PERSIST) {                       // ... or by iteration ev of the persistent node kernel (one poller per CTA)
-      if (t == 0) {
-        wait_flag_ge(A.node_done + 32 * ch, (unsigned)(ev + 1) * A.node_ctas);
-        if (blockIdx.x == 0) PTRACE(A.trace, 4, qe);
+      if (n_ch == 1 || ufirst < num_units) {      // (with chains: nothing to gather here, nothing to wait for)
+        if (t == 0) {
+          wait_flag_ge(A.node_done + 32 * ch, (unsigned)(ev + 1) * (n_ch > 1 ? A.chain_nblk[ch] : A.node_ctas));
+          if (blockIdx.x == 0) PTRACE(A.trace, 4, qe);
+        }
+        asm volatile("bar.sync 3, 128;" ::: "memory");
       }
-      asm volatile("bar.sync 3, 128;" ::: "memory");
     }
     for (int u = ufirst; u < num_units; u += unit_step, ++it) {
       const int m0 = (tile0 + (u >> 1) * 2 + (int)rank) * SUB_M;
@@ -754,11 +756,12 @@ k_edge_fused2_tc(const FusedArgs A, const __grid_constant__ PairMaps maps) {
     // first unit of q + 1.  It drains only when this pair has no unit in q + 1 or the sample ends.
     bool pend = false, pend_last = false;
     int pend_ch = 0, pend_q = 0;
-    auto signal_done = [&](int c, int qq) {   // every o row of this CTA for that chain evaluation is written: tell the node kernel
+    unsigned pend_cnt = 1;
+    auto signal_done = [&](int c, int qq, unsigned cnt) {   // every o row of this CTA for that chain evaluation is written: tell the node kernel
       __threadfence();
       asm volatile("bar.sync 2, 512;" ::: "memory");
       if (threadIdx.x == 0) {
-        red_release_gpu_add(A.edge_done + 32 * c, 1u);
+        red_release_gpu_add(A.edge_done + 32 * c, cnt);
         if (blockIdx.x == 0) PTRACE(A.trace, 7, qq);
       }
     };
@@ -837,12 +840,14 @@ k_edge_fused2_tc(const FusedArgs A, const __grid_constant__ PairMaps maps) {
       }
       if (pend) {
         epi2(it - 1, prev_row, prev_slot);
-        if (PERSIST && pend_last) signal_done(pend_ch, pend_q);
+        if (PERSIST && pend_last) signal_done(pend_ch, pend_q, pend_cnt);
       }
       pend = true; pend_last = u + unit_step >= num_units; pend_ch = ch; pend_q = q;
+      // one count per CTA and evaluation (single chain) or per unit of the chain evaluation (chains)
+      pend_cnt = n_ch > 1 ? (unsigned)((num_units - ufirst + unit_step - 1) / unit_step) : 1u;
       prev_row = row; prev_slot = slot;
     }
-    if (PERSIST && ufirst >= num_units) signal_done(ch, q);     // no unit of this chain evaluation here: nothing to wait for
+    if (PERSIST && n_ch == 1 && ufirst >= num_units) signal_done(ch, q, 1u);   // (single chain: every CTA reports every evaluation)
     bool drain = pend;
     if (PERSIST && pend && q + 1 < n_q) {                       // keep it pending if a unit of q + 1 follows on this pair
       const int cn = n_ch > 1 ? (q + 1) % n_ch : 0;
@@ -853,7 +858,7 @@ k_edge_fused2_tc(const FusedArgs A, const __grid_constant__ PairMaps maps) {
     }
     if (drain) {
       epi2(it - 1, prev_row, prev_slot);
-      if (PERSIST) signal_done(pend_ch, pend_q);
+      if (PERSIST) signal_done(pend_ch, pend_q, pend_cnt);
       pend = false;
     }
     }

@@ -105,6 +105,10 @@ __global__ void __launch_bounds__(NodeTcCfg<M>::THREADS, 1) k_node_tc(const Node
   for (int iter = 0; iter < n_iters; ++iter) {
 #pragma unroll 1
   for (int ch = 0; ch < n_ch; ++ch) {
+  const bool part_mode = PERSIST && n_ch > 1 && A0.node_partition;
+  if (part_mode && ch != (int)(blockIdx.x % n_ch)) continue;               // this CTA serves one chain only
+  const int blk0 = part_mode ? (int)(blockIdx.x / n_ch) : (int)blockIdx.x;
+  const int blk_step = part_mode ? (int)(gridDim.x / n_ch) : (int)gridDim.x;
   NodeArgs A = A0;                       // this iteration's arguments
   const int crow0 = n_ch > 1 ? A0.chain_row0[ch] : 0;                     // rows of this chain: [crow0, cend)
   const int cend = n_ch > 1 ? A0.chain_row0[ch + 1] : A0.n;
@@ -121,7 +125,7 @@ __global__ void __launch_bounds__(NodeTcCfg<M>::THREADS, 1) k_node_tc(const Node
     A.hist = (A0.hist && E.hist_slot >= 0) ? A0.hist + (size_t)E.hist_slot * A0.nP : nullptr;
   }
 #pragma unroll 1
-  for (int blk = blockIdx.x; blk < nblk; blk += PERSIST ? (int)gridDim.x : nblk) {
+  for (int blk = blk0; blk < nblk; blk += PERSIST ? blk_step : nblk) {
   const int row0 = crow0 + blk * C::ROWS;
   const int v = row0 + r;
   if (tid < C::ROW_THREADS) {
@@ -171,7 +175,7 @@ __global__ void __launch_bounds__(NodeTcCfg<M>::THREADS, 1) k_node_tc(const Node
   if (!PERSIST) {
     pdl_wait();                          // o / x / pe are produced (or still read) by the preceding edge kernel
   } else if (need_wait) {                // ... or by evaluation iter - 1 of the persistent edge kernel
-    if (tid == 0) wait_flag_ge(A0.edge_done + 32 * ch, (unsigned)iter * A0.edge_ctas);
+    if (tid == 0) wait_flag_ge(A0.edge_done + 32 * ch, (unsigned)iter * (n_ch > 1 ? 2u * A0.chain_units[ch] : A0.edge_ctas));
     __syncthreads();
     need_wait = false;
     PTRACE(ptr_, 1, tq);
@@ -412,14 +416,19 @@ __global__ void __launch_bounds__(NodeTcCfg<M>::THREADS, 1) k_node_tc(const Node
   ++nblk_done;
   if (PERSIST) __syncthreads();          // the staging rows (= the next block's scratch) are free again
   }
-  if (PERSIST) {                         // x / history / pe of this chain and iteration are written: tell the edge kernel
-    if (need_wait) {                     // (a CTA without blocks in this chain still keeps step with the edge kernel)
-      if (tid == 0) wait_flag_ge(A0.edge_done + 32 * ch, (unsigned)iter * A0.edge_ctas);
+  if (PERSIST && n_ch == 1) {            // x / history / pe of this iteration are written: tell the edge kernel
+    if (need_wait) {                     // (a CTA without a block still keeps step with the edge kernel: the flag counts CTAs)
+      if (tid == 0) wait_flag_ge(A0.edge_done, (unsigned)iter * A0.edge_ctas);
       __syncthreads();
     }
     __threadfence();
     __syncthreads();
-    if (tid == 0) red_release_gpu_add(A0.node_done + 32 * ch, 1u);
+    if (tid == 0) red_release_gpu_add(A0.node_done, 1u);
+    PTRACE(ptr_, 3, tq);
+  } else if (PERSIST && blk0 < nblk) {   // chains: the flag counts blocks; a CTA without a block of this chain stays out of it
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) red_release_gpu_add(A0.node_done + 32 * ch, (unsigned)((nblk - blk0 + blk_step - 1) / blk_step));
     PTRACE(ptr_, 3, tq);
   }
   }

@@ -167,6 +167,9 @@ struct NodeArgs {
   // turn, so a few node CTAs serve all nodes while the edge kernel works on the other chain.  num_chains <= 1: all rows.
   int num_chains;
   int chain_row0[CCSP_MAX_CHAINS + 1];
+  unsigned chain_units[CCSP_MAX_CHAINS];   // edge units of chain c: iteration i may start at edge_done[c] >= i * 2 * chain_units[c]
+  int node_partition;            // 1: CTA b serves chain b % num_chains only (small shards: one block per CTA, the chains' node phases
+                                 // do not queue behind each other); 0: every CTA walks all chains in turn
 };
 
 // per-iteration arguments of the persistent node kernel (what ccsp_sample passes per launch otherwise)

@@ -766,6 +766,9 @@ struct FusedArgs {
   // tensor pipe works on another chain, and the operand pipeline never drains.  num_chains <= 1: one chain = all tiles.
   int num_chains;
   int chain_tile0[CCSP_MAX_CHAINS + 1];
+  unsigned chain_nblk[CCSP_MAX_CHAINS];   // node blocks of chain c: with chains, node_done counts BLOCKS (a chain evaluation may
+                             // gather at (ev + 1) * chain_nblk[c]) and edge_done counts units x 2 CTAs, so a CTA without work in a chain
+                             // evaluation neither waits nor signals and the chains only meet on the SMs they share
   int drain_each_eval;       // 1: epilogue-2 is drained at the end of every chain evaluation (0: carried into the next one)
   unsigned *arrive;          // host-mapped counter, += 1 per CTA at entry (the host launches the node kernel once all are resident)
 };

@@ -15,7 +15,7 @@ from diffusion_ccsp_b200.denoise_fn import ConstraintDiffuser
 lib = _abi.load_library()
 lib.ccsp_debug_trap_info.restype = ctypes.c_uint64
 B, N, T, K = (int(v) for v in sys.argv[1:5])
-ctas = [int(v) for v in sys.argv[5:]] or [24]
+ctas = [int(v) for v in sys.argv[5:]] or [0]
 dims = synthetic.DIMS['qualitative']
 batch = scenes.qualitative_batch(B, N)
 
@@ -55,7 +55,10 @@ a, ms1 = timed(gd, 3)
 print(f'chain-sorted plan, launch per evaluation: {ms1:.4f} ms/evaluation  equal: {same_bits(a, ref)}', flush=True)
 os.environ.pop('CCSP_PERSIST')
 for c in ctas:
-    os.environ['CCSP_PIPE_NODE_CTAS'] = str(c)
+    if c:
+        os.environ['CCSP_PIPE_NODE_CTAS'] = str(c)
+    else:
+        os.environ.pop('CCSP_PIPE_NODE_CTAS', None)
     try:
         _abi.reset_launch_count()
         b, ms2 = timed(gd, 3)

@@ -100,7 +100,7 @@ def run_chains(batch, mode, tri, T, K, chains, node_ctas=None, EBM='ULA', traine
         os.environ.pop('CCSP_PIPE_NODE_CTAS', None)
 
 
-@pytest.mark.parametrize('chains,node_ctas', [(2, 8), (3, 24), (4, 2)])
+@pytest.mark.parametrize('chains,node_ctas', [(2, 8), (3, 24), (4, 2), (2, None), (4, None)])     # None: one node CTA per block and chain
 def test_pipelined_chains_equal_launch_per_evaluation(chains, node_ctas):
     batch = scenes.qualitative_batch(200, 8)                  # 1800 nodes, ~15.8 k edges: several units per pair and chain
     T, K = 8, 4
