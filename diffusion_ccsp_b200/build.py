@@ -25,6 +25,8 @@ NVCC_FLAGS = [
     '-Xcompiler', '-fPIC', '-shared',
     '-Xptxas', '-v',
 ]
+if os.environ.get('CCSP_EXTRA_DEFS'):          # experiments: extra -D flags
+    NVCC_FLAGS += ['-D' + d for d in os.environ['CCSP_EXTRA_DEFS'].split()]
 if os.environ.get('CCSP_DEBUG') == '1':      # development builds: mbarrier spin loops trap after 2^22 polls instead of hanging
     NVCC_FLAGS.append('-DCCSP_DEBUG_SPIN_TRAP')
 

@@ -1,8 +1,9 @@
 #!/bin/bash
 set -u
-O=gpurun_out/r2y; mkdir -p $O; rm -f $O/probe_small.txt
-timeout 600 python -m pytest tests/test_gpu_persistent.py -x -q 2>&1 | tail -4
-for B in "64 8" "128 8" "192 8" "256 8" "384 8" "8 4"; do
-for nc in 2 4; do
-echo "== B N = $B, T=100, chains $nc" | tee -a $O/probe_small.txt; PROBE_CHAINS=$nc timeout 300 python scripts/pipe_probe.py $B 100 10 2>&1 | tee -a $O/probe_small.txt | tail -3
-done; done
+O=gpurun_out/r2z; mkdir -p $O
+timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -k "bf16x3" 2>&1 | tail -3
+timeout 600 python bench.py --steps 3 --warmup 2 --no-cpu-baseline --no-e2e --no-configs 2>$O/bench.err | tee $O/bench_orderB.json | python -c "
+import sys, json
+d = json.loads(sys.stdin.read().strip().splitlines()[-1])
+print({k: d[k] for k in ('value', 'ms_per_step', 'clocks')}, d['roofline']['avg_launch_ms'], d['roofline']['frac'], d['kernels']['avg_ms'])"
+tail -2 $O/bench.err
