@@ -19,7 +19,7 @@ MATH_FP32, MATH_TF32X3, MATH_BF16X3, MATH_TF32, MATH_BF16 = 0, 1, 2, 3, 4
 MATH_NAMES = {'fp32': MATH_FP32, 'tf32x3': MATH_TF32X3, 'bf16x3': MATH_BF16X3, 'tf32': MATH_TF32, 'bf16': MATH_BF16}
 
 EXPORTS = [
-    'ccsp_last_error', 'ccsp_debug_trap_info', 'ccsp_debug_persist_trace', 'ccsp_abi_version', 'ccsp_launch_count', 'ccsp_reset_launch_count',
+    'ccsp_last_error', 'ccsp_debug_trap_info', 'ccsp_debug_persist_trace', 'ccsp_debug_chain_cuts', 'ccsp_abi_version', 'ccsp_launch_count', 'ccsp_reset_launch_count',
     'ccsp_model_create', 'ccsp_model_destroy', 'ccsp_model_set_math', 'ccsp_model_get_math',
     'ccsp_plan_create', 'ccsp_plan_destroy', 'ccsp_plan_num_nodes', 'ccsp_plan_num_edges',
     'ccsp_plan_num_edge_rows', 'ccsp_denoise', 'ccsp_sample',

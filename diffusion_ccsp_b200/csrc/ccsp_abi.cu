@@ -518,6 +518,44 @@ static void ensure_arrival_word() {
 // and TMEM set-up, table loads and the W2 fetch are paid once per sample and the launch gaps disappear.  Same arithmetic in the
 // same order: results are bit-identical to the launch-per-evaluation path (tests/test_gpu_persistent.py).
 // -------------------------------------------------------------------------------------------------------------------------
+// Cut the node range [0, n) into `want` contiguous groups of whole scenes: a cut between nodes s - 1 and s is legal when no
+// (typed) edge has one endpoint on either side; among the legal cuts the k-th is the one whose edge count below it is closest
+// to k / want of all edges.  Returns the group boundaries {0, .., n}; {0, n} when fewer legal cuts exist than asked for.
+static std::vector<int64_t> chain_cuts(int64_t n, int64_t E, const int64_t *edge_index, const std::vector<int> &etype, int want) {
+  std::vector<int64_t> whole = {0, n};
+  if (want <= 1 || n < 2) return whole;
+  std::vector<int> cover(n + 2, 0);
+  std::vector<int64_t> below(n + 2, 0);                     // below[s] = edges with both endpoints < s
+  int64_t Ev = 0;
+  for (int64_t e = 0; e < E; ++e) {
+    if (etype[e] < 0) continue;
+    const int64_t i = edge_index[e], j = edge_index[E + e];
+    const int64_t lo = std::min(i, j), hi = std::max(i, j);
+    ++cover[lo + 1]; --cover[hi + 1];
+    ++below[hi + 1];
+    ++Ev;
+  }
+  if (Ev == 0) return whole;
+  for (int64_t s2 = 1; s2 <= n; ++s2) { cover[s2] += cover[s2 - 1]; below[s2] += below[s2 - 1]; }
+  std::vector<int64_t> out = {0};
+  int64_t prev = 0;
+  for (int k = 1; k < want; ++k) {
+    const int64_t target = Ev * k / want;
+    int64_t best = -1, best_d = -1;
+    for (int64_t s2 = prev + 1; s2 < n; ++s2) {
+      if (cover[s2] != 0) continue;                         // an edge spans the cut between nodes s2 - 1 and s2
+      const int64_t d = std::llabs(below[s2] - target);
+      if (best < 0 || d < best_d) { best = s2; best_d = d; }
+      if (below[s2] > target) break;
+    }
+    if (best < 0) return whole;
+    out.push_back(best);
+    prev = best;
+  }
+  out.push_back(n);
+  return out;
+}
+
 extern "C" { static int drain_timing(CcspPlan *p); }
 struct PersistCfg {
   int pairs = 0;        // CTA pairs of the persistent edge kernel
@@ -710,6 +748,22 @@ unsigned long long ccsp_debug_trap_info(void) { return g_trap_host ? g_trap_host
 unsigned long long ccsp_debug_persist_trace(int event, int iter) {
   return (g_trap_host && event >= 0 && event < 12 && iter >= 0 && iter < 32) ? g_trap_host[8 + event * 32 + iter] : 0ull;
 }
+/* developer aid / host-logic test hook (no device needed): the scene-group boundaries ccsp_plan_create would use for `want` chains */
+int ccsp_debug_chain_cuts(const int64_t *edge_index, const float *edge_attr, int64_t n, int64_t E, int32_t num_types, int32_t want,
+                          int64_t *bounds_out) {
+  if (!bounds_out || n <= 0 || E < 0 || (E > 0 && (!edge_index || !edge_attr)) || want < 1 || want > CCSP_MAX_CHAINS) return -1;
+  std::vector<int> etype(E);
+  for (int64_t e = 0; e < E; ++e) {
+    const float a = edge_attr[e];
+    int c = (a >= 0.f && a < (float)num_types) ? (int)a : -1;
+    if (c >= 0 && (float)c != a) c = -1;
+    if (c >= 0 && (edge_index[e] < 0 || edge_index[e] >= n || edge_index[E + e] < 0 || edge_index[E + e] >= n)) return -1;
+    etype[e] = c;
+  }
+  const std::vector<int64_t> b = chain_cuts(n, E, edge_index, etype, want);
+  for (size_t i = 0; i < b.size(); ++i) bounds_out[i] = b[i];
+  return (int)b.size() - 1;
+}
 int ccsp_abi_version(void) { return CCSP_ABI_VERSION; }
 uint64_t ccsp_launch_count(void) { return g_launches; }
 void ccsp_reset_launch_count(void) { g_launches = 0; }
@@ -784,48 +838,12 @@ int ccsp_plan_create(CcspModel *m, const float *x, int64_t n, int32_t F, const i
   // The pipelined sampling path (sample_persistent) interleaves the chains: while the node kernel updates the nodes of one
   // chain, the edge kernel works on another.  Rows are grouped (chain, type); within a node the accumulation order is
   // unchanged (a node's edges all lie in its own chain, still type-major in edge order).
-  std::vector<int64_t> chain_node0 = {0, n};
-  {
-    int64_t Ev = 0;
-    for (int c = 0; c < C; ++c) Ev += cnt[c];
-    // Opt-in (CCSP_CHAINS=2..4): measured on B200 the pipelined path is no faster than two launches per evaluation at any
-    // batch size (profiles/README.md R2.8) — the SMs it takes from the edge phase for the node CTAs cost what the hidden
-    // node phase and ramps save — and every extra chain pads every type once more (+2 % rows per chain at config 2).
-    int want = 1;
-    if (const char *env = getenv("CCSP_CHAINS")) want = std::max(1, std::min(CCSP_MAX_CHAINS, atoi(env)));
-    if (want > 1 && Ev > 0) {
-      std::vector<int> cover(n + 2, 0);
-      std::vector<int64_t> below(n + 2, 0);                   // below[s] = edges with both endpoints < s
-      for (int64_t e = 0; e < E; ++e) {
-        if (etype[e] < 0) continue;
-        const int64_t i = edge_index[e], j = edge_index[E + e];
-        const int64_t lo = std::min(i, j), hi = std::max(i, j);
-        ++cover[lo + 1]; --cover[hi + 1];
-        ++below[hi + 1];
-      }
-      for (int64_t s2 = 1; s2 <= n; ++s2) { cover[s2] += cover[s2 - 1]; below[s2] += below[s2 - 1]; }
-      std::vector<int64_t> cuts;
-      int64_t prev = 0;
-      for (int k = 1; k < want; ++k) {
-        const int64_t target = Ev * k / want;
-        int64_t best = -1, best_d = -1;
-        for (int64_t s2 = prev + 1; s2 < n; ++s2) {
-          if (cover[s2] != 0) continue;                       // an edge spans the cut between nodes s2 - 1 and s2
-          const int64_t d = std::llabs(below[s2] - target);
-          if (best < 0 || d < best_d) { best = s2; best_d = d; }
-          if (below[s2] > target) break;
-        }
-        if (best < 0) break;
-        cuts.push_back(best);
-        prev = best;
-      }
-      if ((int)cuts.size() == want - 1) {
-        chain_node0.assign(1, 0);
-        for (int64_t c2 : cuts) chain_node0.push_back(c2);
-        chain_node0.push_back(n);
-      }
-    }
-  }
+  int want_chains = 1;
+  // Opt-in (CCSP_CHAINS=2..4): measured on B200 the pipelined path is no faster than two launches per evaluation at any
+  // batch size (profiles/README.md R2.8) — the SMs it takes from the edge phase for the node CTAs cost what the hidden
+  // node phase and ramps save — and every extra chain pads every type once more (+2 % rows per chain at config 2).
+  if (const char *env = getenv("CCSP_CHAINS")) want_chains = std::max(1, std::min(CCSP_MAX_CHAINS, atoi(env)));
+  const std::vector<int64_t> chain_node0 = chain_cuts(n, E, edge_index, etype, want_chains);
   const int NC = (int)chain_node0.size() - 1;
   auto chain_of = [&](int64_t v) { int c = 0; while (c + 1 < NC && v >= chain_node0[c + 1]) ++c; return c; };
   std::vector<int64_t> gcnt((size_t)NC * C, 0);

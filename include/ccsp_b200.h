@@ -109,6 +109,12 @@ const char *ccsp_last_error(void);
 unsigned long long ccsp_debug_trap_info(void);
 /* developer aid (CCSP_PERSIST_TRACE=1): global-timer timeline of the persistent kernels, [event 0..7][iteration 0..31], ns */
 unsigned long long ccsp_debug_persist_trace(int event, int iter);
+/* Host-only (no device): the node-range boundaries {0, .., n} of the `want` (1..4) independent scene groups ("chains") that
+ * ccsp_plan_create cuts a batch into when CCSP_CHAINS is set (a PyG batch is a disjoint union of scene graphs: the property
+ * `Batch.batch` encodes in the reference, networks/denoise_fn.py:466-508 never crosses scenes).  bounds_out holds want + 1
+ * entries; returns the number of groups (1 when the graph cannot be cut that often), -1 on bad arguments. */
+int ccsp_debug_chain_cuts(const int64_t *edge_index, const float *edge_attr, int64_t n, int64_t E, int32_t num_types, int32_t want,
+                          int64_t *bounds_out);
 int ccsp_abi_version(void);
 /* Number of kernels launched by this library on the calling thread since the last reset (bench.py's
  * `gpu_launches`). */

@@ -149,3 +149,47 @@ def test_analysis_methods_match_the_reference():
             out = out / torch.sqrt(cnt)[:, None]
             out[batch.mask.bool()] = batch.x[:, -P:][batch.mask.bool()]
         assert torch.allclose(out, want, rtol=0, atol=1e-6)
+
+
+# ---- host logic of the pipelined-chains plan layout (runs without a device): where ccsp_plan_create cuts a batch -----------------
+def _chain_cuts(lib_path, batch, want, num_types=13):
+    import numpy as np
+    lib = ctypes.CDLL(lib_path)
+    lib.ccsp_debug_chain_cuts.restype = ctypes.c_int
+    ei = batch.edge_index.to(torch.int64).contiguous()
+    ea = batch.edge_attr.to(torch.float32).contiguous()
+    out = np.zeros(want + 1, dtype=np.int64)
+    k = lib.ccsp_debug_chain_cuts(ctypes.c_void_p(ei.data_ptr()), ctypes.c_void_p(ea.data_ptr()), ctypes.c_int64(batch.num_nodes),
+                                  ctypes.c_int64(ei.shape[1]), ctypes.c_int32(num_types), ctypes.c_int32(want),
+                                  ctypes.c_void_p(out.ctypes.data))
+    return k, out[:k + 1].tolist()
+
+
+@pytest.mark.parametrize('want', [2, 3, 4])
+def test_chain_cuts_fall_between_scenes_and_balance_the_edges(lib_path, want):
+    from diffusion_ccsp_b200 import scenes
+    batch = scenes.qualitative_batch(40, 8)
+    k, bounds = _chain_cuts(lib_path, batch, want)
+    assert k == want and bounds[0] == 0 and bounds[-1] == batch.num_nodes and bounds == sorted(set(bounds))
+    starts = set(batch.scene_node_ranges().tolist())
+    assert all(b in starts for b in bounds)                       # only whole scenes
+    i, j = batch.edge_index[0], batch.edge_index[1]
+    per_chain = []
+    for c in range(k):
+        inside_i = (i >= bounds[c]) & (i < bounds[c + 1])
+        inside_j = (j >= bounds[c]) & (j < bounds[c + 1])
+        assert bool((inside_i == inside_j).all())                 # no edge crosses a cut
+        per_chain.append(int(inside_i.sum()))
+    assert sum(per_chain) == batch.num_edges
+    assert max(per_chain) - min(per_chain) <= 2 * 90              # balanced to within about a scene (<= 90 edges at N = 8)
+
+
+def test_chain_cuts_degenerate_cases(lib_path):
+    from diffusion_ccsp_b200 import scenes
+    one = scenes.qualitative_batch(1, 4)
+    assert _chain_cuts(lib_path, one, 2) == (1, [0, one.num_nodes])         # a single scene cannot be cut
+    two = scenes.qualitative_batch(2, 4)
+    k, bounds = _chain_cuts(lib_path, two, 2)
+    assert k == 2 and bounds[1] == int(two.scene_node_ranges()[1])
+    assert _chain_cuts(lib_path, two, 4)[0] == 1                            # fewer legal cuts than asked for: stay whole
+    assert _chain_cuts(lib_path, two, 1) == (1, [0, two.num_nodes])
