@@ -35,15 +35,17 @@ def main():
     ap.add_argument('--init', default=None, help='state dict (.pt) to start from')
     ap.add_argument('--lr', type=float, default=5e-4)
     ap.add_argument('--max-tiles', type=int, default=8, help='train only on scenes with at most this many tiles (the reference trains on 2-5)')
+    ap.add_argument('--min-tiles', type=int, default=2, help='train only on scenes with at least this many tiles')
     ap.add_argument('--cosine', action='store_true', help='cosine decay of the learning rate to 2 % of --lr over --steps (the reference trains at a constant rate)')
     a = ap.parse_args()
     torch.manual_seed(a.seed)
     train_pool = scenes.qualitative_train_pool()                      # 24 000 scenes, 2..8 tiles (tests/golden/make_train_pool.py)
-    if a.max_tiles < 8:
+    if a.max_tiles < 8 or a.min_tiles > 2:
         off = train_pool.scene_node_ranges()
-        keep = np.where(np.diff(off) - 1 <= a.max_tiles)[0]
+        tiles = np.diff(off) - 1
+        keep = np.where((tiles <= a.max_tiles) & (tiles >= a.min_tiles))[0]
         train_pool = scenes._gather_scenes_fast(train_pool, keep)
-        print(f'[fixture] training on {train_pool.num_graphs} scenes with <= {a.max_tiles} tiles', flush=True)
+        print(f'[fixture] training on {train_pool.num_graphs} scenes with {a.min_tiles}..{a.max_tiles} tiles', flush=True)
     eval_batch = scenes.qualitative_batch(a.eval_scenes, 8)           # evaluation fixtures: disjoint draws
     eval4 = scenes.qualitative_batch(64, 4)
     dims = synthetic.DIMS['qualitative']
