@@ -18,7 +18,7 @@
 // k-step because it queues behind the next GEMM1 on the tensor pipe, and the stall propagates to epilogue-1 through the
 // operand slots.  fused2's double-buffered D2 + deferred epilogue-2 hides exactly that latency.
 #pragma once
-#include "kernels_fused2.cuh"
+#include "../kernels_fused2.cuh"
 
 namespace ccsp {
 namespace tc {

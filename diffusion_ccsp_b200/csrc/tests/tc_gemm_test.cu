@@ -10,7 +10,7 @@
 
 #include "../kernels_tc.cuh"
 #include "../kernels_fused2.cuh"
-#include "../kernels_fused3.cuh"
+#include "kernels_fused3.cuh"
 
 namespace ccsp {
 void set_error(const std::string &) {}
