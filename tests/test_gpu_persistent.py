@@ -132,3 +132,26 @@ def test_chain_cut_needs_independent_scene_groups():
     batch = scenes.qualitative_batch(1, 4)
     out, launches = run_chains(batch, 'qualitative', False, 3, 2, 2, trained=True, seed=1)
     assert launches - (1 + 2 * 3 * 3) in (0, 2) and bool(torch.isfinite(out).all())
+
+
+def test_pipelined_chains_report_kernel_timing():
+    """bench.py's roofline leg on the pipelined path: the persistent edge kernel is bracketed by one event pair and booked as
+    `evaluations` samples, so avg = duration / evaluations"""
+    batch = scenes.qualitative_batch(200, 8)
+    dims = synthetic.DIMS['qualitative']
+    den = ConstraintDiffuser(dims=dims, input_mode='qualitative', device='cuda', verbose=False, math='bf16x3')
+    T, K = 6, 4
+    gd = GaussianDiffusion(den, timesteps=T, EBM='ULA', samples_per_step=K).eval()
+    gd.load_state_dict(synthetic.load_trained_checkpoint(), strict=False)
+    os.environ['CCSP_CHAINS'] = '2'
+    try:
+        plan = den.plan_for(batch)
+        plan.set_timing(1)
+        gd.sample(batch, seed=3)
+        gd.sample(batch, seed=4)
+        tm = plan.get_timing()
+        plan.set_timing(0)
+    finally:
+        os.environ.pop('CCSP_CHAINS', None)
+    assert tm['samples'] == 2 * T * (1 + K)
+    assert 0.0 < tm['ms_edge_l1'] / tm['samples'] < 1.0 and tm['ms_node'] == 0.0
