@@ -15,7 +15,7 @@
 //            pieces of the A operand (hi and lo BF16, SWIZZLE_64B) in shared memory;
 //   phase 2  one thread issues the 128 x 256 x 128 GEMM (3-term split, FP32 accumulate in TMEM) against W2, which
 //            a single thread fetched with cp.async.bulk while phase 1 ran;
-//   phase 3  8 warps: TMEM -> + b2 -> SiLU -> hi/lo -> the node's row of pe_split.
+//   phase 3  16 warps: TMEM -> + b2 -> SiLU -> hi/lo -> the node's row of pe_split.
 #pragma once
 #include "kernels_fused2.cuh"
 #include "kernels_simt.cuh"
@@ -26,7 +26,7 @@ namespace tc {
 template <class M>
 struct NodeTcCfg {
   static_assert(M::KIND == KIND_BF16, "BF16 operand modes only");
-  static constexpr int ROWS = 64;                             // nodes per CTA (rows 64..127 of the M = 128 MMA are idle)
+  static constexpr int ROWS = 64;                             // nodes per CTA (rows 64..127 of the M = 128 MMA repeat them)
   static constexpr int NKC = CCSP_HH / M::KC;                 // 128 / 32 = 4 k-chunks
   static constexpr int B_STAGE = M::NS * CCSP_H * ROWB;       // 256 weight rows x 64 B (x2 parts): 32 KB
   static constexpr int OFF_B = NKC * M::A_STAGE;
@@ -338,11 +338,16 @@ __global__ void __launch_bounds__(NodeTcCfg<M>::THREADS, 1) k_node_tc(const Node
       uint8_t *dst = a_stage + sw64_off(r, q);
       *reinterpret_cast<uint4 *>(dst) = hi;
       if (M::NS == 2) *reinterpret_cast<uint4 *>(dst + PART) = lo;
+      // rows 64..127 of the M = 128 MMA repeat the 64 nodes: TMEM lanes 64..127 then hold the same results, and the warps that
+      // own those lanes take half of every node's columns in phase 3 (a warp can only read its own 32 lanes)
+      uint8_t *dup = a_stage + sw64_off(r + C::ROWS, q);
+      *reinterpret_cast<uint4 *>(dup) = hi;
+      if (M::NS == 2) *reinterpret_cast<uint4 *>(dup + PART) = lo;
     }
     fence_proxy_async();
   }
   NTR(5);
-  __syncthreads();                       // A operand complete (rows 64..127 are never read back)
+  __syncthreads();                       // A operand complete
   NTR(6);
 
   if (tid == C::ROW_THREADS) {
@@ -357,24 +362,25 @@ __global__ void __launch_bounds__(NodeTcCfg<M>::THREADS, 1) k_node_tc(const Node
     }
     umma_commit(tfull);
     NTR(8);
-  } else if (tid < C::ROW_THREADS && (warp & 3) < 2) {
-    // ---- phase 3: warp w <-> TMEM lanes 32 (w & 3).. (only lanes 0..63 hold nodes), columns 64 (w >> 2).. +63 ----
-    const int quarter = warp & 3, cg = warp >> 2;
-    const int rr = quarter * 32 + lane, vv = row0 + rr;
+  } else if (tid < C::ROW_THREADS) {
+    // ---- phase 3: warp w <-> TMEM lanes 32 (w & 3).. = node (w & 1) * 32 + lane (lanes 64..127 repeat the nodes), columns
+    //      64 (w >> 2) + 32 ((w & 3) >> 1) .. +31: all 16 warps work, 32 columns each ----
+    const int quarter = warp & 3, cg = warp >> 2, chalf = quarter >> 1;
+    const int rr = (quarter & 1) * 32 + lane, vv = row0 + rr;
     mbar_wait(tfull, nblk_done & 1);
     NTR(7);
     tc_fence_after();
-    const uint32_t taddr = tmem_base + cg * 64 + ((uint32_t)(quarter * 32) << 16);
+    const uint32_t taddr = tmem_base + cg * 64 + chalf * 32 + ((uint32_t)(quarter * 32) << 16);
     // results are staged row-major in shared memory (the A operand region is free now) and written out coalesced:
     // a lane-per-row store of 16 B at a 1 KB stride costs one L1 pass per lane, 4096 of them per CTA
     uint8_t *orow = smem + (size_t)rr * M::PE_ROW_BYTES;
 #pragma unroll 1                          // rolled, 16 columns per iteration (see phase 1c)
-    for (int c16 = 0; c16 < 4; ++c16) {
+    for (int c16 = 0; c16 < 2; ++c16) {
       float vals[16];
       tmem_ld16(taddr + c16 * 16, vals);
 #pragma unroll
       for (int h8 = 0; h8 < 2; ++h8) {
-        const int c0 = cg * 64 + c16 * 16 + h8 * 8;
+        const int c0 = cg * 64 + chalf * 32 + c16 * 16 + h8 * 8;
         float f[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
