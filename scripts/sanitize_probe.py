@@ -36,3 +36,11 @@ em.to('cuda')
 g, e = em(torch.randn(b.num_nodes, 4), b, torch.tensor([5]), tag='EBM')
 torch.cuda.synchronize()
 print('energy', float(e), 'ok')
+# the sampling kernels themselves (node + fused edge kernel, BF16x3 and FP32 modes), ragged batch, a few evaluations
+for math in ('bf16x3', 'fp32'):
+    sm = ConstraintDiffuser(dims=dims, input_mode='qualitative', device='cuda', verbose=False, math=math)
+    sgd = GaussianDiffusion(sm, timesteps=3, EBM='ULA', samples_per_step=2).eval()
+    sgd.load_state_dict(synthetic.make_state_dict(dims, 'qualitative', seed=1), strict=False)
+    out = sgd.sample(b, seed=7)
+    torch.cuda.synchronize()
+    print('sample', math, 'finite', bool(torch.isfinite(out).all()))
