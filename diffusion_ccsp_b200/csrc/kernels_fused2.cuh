@@ -435,6 +435,23 @@ k_edge_fused2_tc(const FusedArgs A, const __grid_constant__ PairMaps maps) {
     // when all its earlier cp.async have landed), so a thread never waits for data and all NSTAGE1 stages can be
     // in flight; the peer's barrier is forwarded to the leader by the relay lane below.
     uint32_t g = 0, it = 0;
+    uint32_t roff[NP];                   // row offsets in 16-byte units (row stride 1 KB: fits 32 bits up to 4 M nodes)
+    uint32_t live = 0;                   // bit p: row p of this thread is a real edge
+    auto load_rows = [&](const int *idx, int m0) {
+      live = 0;
+#pragma unroll
+      for (int p = 0; p < NP; ++p) {
+        const int ix = __ldg(&idx[m0 + r0 + RPP * p]);
+        roff[p] = (uint32_t)ix * (M::PE_ROW_BYTES / 16);
+        live |= (ix + 1 != A.pad_row_plus1 ? 1u : 0u) << p;      // padded rows are zero-filled without touching memory
+      }
+    };
+    // the first unit's edge indices are plan constants: fetched under the tail of the preceding node kernel
+    bool preloaded = false;
+    if (!PERSIST && unit0 < num_units_all) {
+      load_rows(A.src_i, ((unit0 >> 1) * 2 + (int)rank) * SUB_M);
+      preloaded = true;
+    }
     if (!PERSIST) pdl_wait();            // pe_split is written by the preceding node kernel
     int cbase = 0;
     for (int qe = 0; qe < n_q; ++qe) {   // (q is this thread's piece index)
@@ -450,19 +467,11 @@ k_edge_fused2_tc(const FusedArgs A, const __grid_constant__ PairMaps maps) {
     }
     for (int u = ufirst; u < num_units; u += unit_step, ++it) {
       const int m0 = (tile0 + (u >> 1) * 2 + (int)rank) * SUB_M;
-      uint32_t roff[NP];                 // row offsets in 16-byte units (row stride 1 KB: fits 32 bits up to 4 M nodes)
-      uint32_t live = 0;                 // bit p: row p of this thread is a real edge
 #pragma unroll 1
       for (int kc = 0; kc < M::NKC1; ++kc, ++g) {
         if (kc == 0 || kc == M::NKC1 / 2) {
-          const int *idx = kc == 0 ? A.src_i : A.src_j;
-          live = 0;
-#pragma unroll
-          for (int p = 0; p < NP; ++p) {
-            const int ix = __ldg(&idx[m0 + r0 + RPP * p]);
-            roff[p] = (uint32_t)ix * (M::PE_ROW_BYTES / 16);
-            live |= (ix + 1 != A.pad_row_plus1 ? 1u : 0u) << p;      // padded rows are zero-filled without touching memory
-          }
+          if (kc == 0 && preloaded) preloaded = false;
+          else load_rows(kc == 0 ? A.src_i : A.src_j, m0);
         }
         const uint32_t s = g % C::NSTAGE1;
         mbar_wait(&empty1[s], ((g / C::NSTAGE1) & 1) ^ 1);
