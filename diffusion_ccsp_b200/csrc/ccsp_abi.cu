@@ -188,6 +188,7 @@ struct CcspPlan {
   // persistent small-shard path (sample_persistent): two side streams, their events, the flag pair, device schedule arrays
   cudaStream_t ps_node = nullptr, ps_edge = nullptr;
   cudaEvent_t pe_begin = nullptr, pe_node = nullptr, pe_edge = nullptr, pe_t0 = nullptr, pe_t1 = nullptr;
+  unsigned *arrive_host = nullptr, *arrive_dev = nullptr;   // host-mapped: CTAs of the persistent edge kernel that have started
   int persist_timed_evals = 0;    // > 0: pe_t0 / pe_t1 bracket a persistent edge kernel that ran this many evaluations
   unsigned *p_flags = nullptr;
   NodeEval *p_sched = nullptr;
@@ -501,13 +502,15 @@ static void ensure_trap_word() {
   }
 }
 
-// host-mapped arrival counter of the persistent edge kernel (one increment per CTA at entry)
-static unsigned *g_arrive_host = nullptr, *g_arrive_dev = nullptr;
-static void ensure_arrival_word() {
-  if (g_arrive_host) return;
-  if (cudaHostAlloc((void **)&g_arrive_host, 64, cudaHostAllocMapped) != cudaSuccess) { g_arrive_host = nullptr; return; }
-  *g_arrive_host = 0;
-  if (cudaHostGetDevicePointer((void **)&g_arrive_dev, g_arrive_host, 0) != cudaSuccess) g_arrive_dev = nullptr;
+// host-mapped arrival counter of a plan's persistent edge kernel (one increment per CTA at entry); owned by the plan
+static void ensure_arrival_word(CcspPlan *p) {
+  if (p->arrive_host) return;
+  if (cudaHostAlloc((void **)&p->arrive_host, 64, cudaHostAllocMapped) != cudaSuccess) { p->arrive_host = nullptr; return; }
+  *p->arrive_host = 0;
+  if (cudaHostGetDevicePointer((void **)&p->arrive_dev, p->arrive_host, 0) != cudaSuccess) {
+    cudaFreeHost(p->arrive_host);
+    p->arrive_host = p->arrive_dev = nullptr;
+  }
 }
 
 // -------------------------------------------------------------------------------------------------------------------------
@@ -676,8 +679,8 @@ static int sample_persistent(CcspPlan *p, const CcspSchedule *s, const CcspNoise
   unsigned *node_done = p->p_flags, *edge_done = p->p_flags + 32 * CCSP_MAX_CHAINS;
   // the edge clusters must all be resident before the node CTAs take SMs: they need whole TPCs, and a node CTA that got there
   // first would leave a cluster waiting for a TPC that never frees up (both kernels run until the sample is done)
-  ensure_arrival_word();
-  if (g_arrive_host) *g_arrive_host = 0;
+  ensure_arrival_word(p);
+  if (p->arrive_host) *p->arrive_host = 0;
   // both functions are loaded before either runs (lazy module loading would otherwise stall the second launch behind the first kernel)
   CCSP_CUDA_TRY((tc::configure_node_tc_persistent<M>()));
   // ---- the edge kernel first: its clusters take whole TPCs -------------------------------------------------------------------
@@ -696,7 +699,7 @@ static int sample_persistent(CcspPlan *p, const CcspSchedule *s, const CcspNoise
     a.node_done = node_done; a.edge_done = edge_done; a.node_ctas = node_ctas;
     a.num_chains = NC;
     for (int c = 0; c <= NC; ++c) a.chain_tile0[c] = p->chain_tile0[c];
-    a.arrive = g_arrive_dev;
+    a.arrive = p->arrive_dev;
     for (int c = 0; c < NC; ++c) a.chain_nblk[c] = (unsigned)((p->chain_row0[c + 1] - p->chain_row0[c] + 63) / 64);
     // carry epilogue-2 across chain evaluations only where a pair has several units per chain evaluation to hide it behind
     a.drain_each_eval = (NC == 1 || cfg.partition || getenv("CCSP_PIPE_DRAIN")) ? 1 : 0;
@@ -706,10 +709,10 @@ static int sample_persistent(CcspPlan *p, const CcspSchedule *s, const CcspNoise
     if (p->timing_stride > 0) { CCSP_CUDA_TRY(cudaEventRecord(p->pe_t1, p->ps_edge)); p->persist_timed_evals = num_evals; }
     count_launch();
   }
-  if (NC > 1 && g_arrive_host) {
+  if (NC > 1 && p->arrive_host) {
     // wait (host) until every edge CTA has started; bounded: after 20 s go on and let the flag waits' own trap decide
     const auto t0 = std::chrono::steady_clock::now();
-    while (*(volatile unsigned *)g_arrive_host < (unsigned)(2 * pairs)) {
+    while (*(volatile unsigned *)p->arrive_host < (unsigned)(2 * pairs)) {
       if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 20.0) break;
     }
   }
@@ -989,6 +992,7 @@ void ccsp_plan_destroy(CcspPlan *p) {
   if (p->pe_edge) cudaEventDestroy(p->pe_edge);
   if (p->pe_t0) cudaEventDestroy(p->pe_t0);
   if (p->pe_t1) cudaEventDestroy(p->pe_t1);
+  if (p->arrive_host) cudaFreeHost(p->arrive_host);
   p->pool.free_all();
   delete p;
   cudaSetDevice(prev);
